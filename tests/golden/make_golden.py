@@ -1,0 +1,108 @@
+"""Generate the committed golden fixtures from the COMPILED REFERENCE (oracle/_ref/ref_driver, built by
+oracle/Makefile from the unmodified sources under /root/reference).  Run only where /root/reference exists:
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Everything written here is an output of the reference's own code; nothing comes from this repo's kernels or
+from oracle/mw_oracle.c.  Fixtures are .npz (fp64, exact) and kept small.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import _oracle as O  # noqa: E402
+
+
+def run_states(tmp, nx, ny, nz, xlen, ylen, zlen, tracers, steps, **mods):
+    r = O.ref_run(tmp, nx=nx, ny=ny, nz=nz, xlen=xlen, ylen=ylen, zlen=zlen, steps=steps, tracers=tracers,
+                  out0=tmp + "/s0.bin", out=tmp + "/s1.bin", bg=tmp + "/bg.bin", precl=tmp + "/precl.bin", **mods)
+    meta = r[-1]
+    T = meta["num_tracers"]
+    s0 = np.fromfile(tmp + "/s0.bin").reshape(5 + T, nz, ny, nx)
+    s1 = np.fromfile(tmp + "/s1.bin").reshape(5 + T, nz, ny, nx)
+    bg = np.fromfile(tmp + "/bg.bin")
+    return s0, s1, bg, meta
+
+
+def main():
+    tmp = tempfile.mkdtemp()
+    # --- config 1: shipped supercell_example grid (100 x 1 x 40, 2-D), Kessler tracers -----------------------
+    g = dict(nx=100, ny=1, nz=40, xlen=1e5, ylen=1e5, zlen=2e4)
+    s0, s1, bg, meta = run_states(tmp, tracers="kessler", steps=10, **g)
+    np.savez_compressed(HERE + "/config1_dycore10.npz", s0=s0, s1=s1, bg=bg, dt=meta["dt"], steps=10, **g)
+    s0, s1, bg, meta = run_states(tmp, tracers="kessler", steps=10, micro=1, sponge=1, nudge=1, **g)
+    np.savez_compressed(HERE + "/config1_full10.npz", s0=s0, s1=s1, bg=bg, dt=meta["dt"], steps=10, **g)
+    # Kessler is inert for the first ~400 steps: make a restart state with cloud and rain (1000 full steps)
+    s0, s1000, bg, meta = run_states(tmp, tracers="kessler", steps=1000, micro=1, sponge=1, nudge=1, **g)
+    s1000.tofile(tmp + "/restart.bin")
+    r = O.ref_run(tmp, tracers="kessler", steps=10, micro=1, sponge=1, nudge=1, perturb=0, **g,
+                  **{"in": tmp + "/restart.bin"}, out=tmp + "/s2.bin", precl=tmp + "/precl.bin")
+    s1010 = np.fromfile(tmp + "/s2.bin").reshape(s1000.shape)
+    precl = np.fromfile(tmp + "/precl.bin")
+    # NOTE: the column nudger's target column is the unperturbed initial column (set before `in=` is loaded)
+    np.savez_compressed(HERE + "/config1_restart1000_full10.npz", s_init=s0, s0=s1000, s1=s1010, precl=precl, bg=bg,
+                        dt=meta["dt"], steps=10, **g)
+    # micro only, one step from the restart (isolates Kessler)
+    r = O.ref_run(tmp, tracers="kessler", steps=1, dycore=0, micro=1, perturb=0, dt=meta["dt"], **g,
+                  **{"in": tmp + "/restart.bin"}, out=tmp + "/s3.bin", precl=tmp + "/precl.bin")
+    np.savez_compressed(HERE + "/config1_restart1000_micro1.npz", s0=s1000,
+                        s1=np.fromfile(tmp + "/s3.bin").reshape(s1000.shape), precl=np.fromfile(tmp + "/precl.bin"),
+                        dt=meta["dt"], **g)
+    # --- small 3-D box, vapour tracer only (the dry-dycore configuration of BASELINE config 2, scaled down) ---
+    g = dict(nx=24, ny=20, nz=16, xlen=24e3, ylen=20e3, zlen=16e3)
+    s0, s1, bg, meta = run_states(tmp, tracers="vapor", steps=5, **g)
+    np.savez_compressed(HERE + "/box3d_vapor_dycore5.npz", s0=s0, s1=s1, bg=bg, dt=meta["dt"], steps=5, **g)
+    g = dict(nx=20, ny=12, nz=12, xlen=20e3, ylen=12e3, zlen=12e3)
+    s0, s1, bg, meta = run_states(tmp, tracers="kessler", steps=4, micro=1, sponge=1, nudge=1, **g)
+    np.savez_compressed(HERE + "/box3d_kessler_full4.npz", s0=s0, s1=s1, bg=bg, dt=meta["dt"], steps=4, **g)
+
+    # --- WENO5 known-answer vectors through WenoLimiter<5> + reconstruct_gll_values ---------------------------
+    rng = np.random.default_rng(20261017)
+    st = [rng.standard_normal((128, 5)), 1e-3 * rng.standard_normal((64, 5)) + 1.0,
+          np.zeros((1, 5)), np.ones((1, 5)) * 3.5, np.array([[0, 0, 1, 0, 0.0]]), np.array([[0, 0, 0, 1, 1.0]]),
+          1e-12 * rng.standard_normal((32, 5)), 1e4 * rng.standard_normal((32, 5)),
+          np.linspace(0, 1, 5)[None, :] ** 2, np.array([[1e-30, 0, 0, 0, 0]])]
+    st = np.ascontiguousarray(np.concatenate(st))
+    st.tofile(tmp + "/st.bin")
+    subprocess.check_call([O.REF_DRIVER, "weno", str(st.shape[0]), tmp + "/st.bin", tmp + "/gll.bin"],
+                          stdout=subprocess.DEVNULL)
+    np.savez_compressed(HERE + "/weno5_kat.npz", stencils=st, gll=np.fromfile(tmp + "/gll.bin").reshape(-1, 2))
+
+    # --- Kessler column known-answers: hand-built supersaturated / rainy columns, rainsplit > 1 --------------
+    nz, ncol, dt = 40, 16, 150.0
+    k = np.arange(nz)[:, None] * np.ones((1, ncol))
+    z = (k + 0.5) * 500.0
+    pk = 1.0 - 9.81 * z / (1003.0 * 300.0)                      # Exner of a 300 K isentropic column
+    rho = 1.0e5 * pk ** (1003.0 / 287.0) / (287.0 * 300.0 * pk)
+    theta = 300.0 + 2.0 * rng.random((nz, ncol))
+    qv = 0.016 * np.exp(-z / 2500.0) * (0.6 + 0.8 * rng.random((nz, ncol)))
+    qc = np.where((z > 1500) & (z < 6000), 2.5e-3 * rng.random((nz, ncol)), 0.0)
+    qr = np.where(z < 7000, 4.0e-3 * rng.random((nz, ncol)), 0.0)
+    qr[:, :2] = 0.0
+    qc[:, 1] = 0.0
+    inp = np.ascontiguousarray(np.stack([theta, qv, qc, qr, rho, pk]))
+    inp.tofile(tmp + "/kin.bin")
+    subprocess.check_call([O.REF_DRIVER, "kessler", str(nz), str(ncol), repr(dt), tmp + "/kin.bin", tmp + "/kout.bin"],
+                          stdout=subprocess.DEVNULL)
+    ko = np.fromfile(tmp + "/kout.bin")
+    np.savez_compressed(HERE + "/kessler_columns_kat.npz", inp=inp, out=ko[:4 * nz * ncol].reshape(4, nz, ncol),
+                        precl=ko[4 * nz * ncol:], dt=dt, dz=500.0)
+
+    # --- ponni MLP 5 -> 10 -> LeakyReLU(0.1) -> 4, fp32, random-init weights --------------------------------
+    w = rng.uniform(-0.5, 0.5, 104).astype(np.float32)
+    x = rng.uniform(-0.2, 1.2, (5, 256)).astype(np.float32)
+    w.astype(np.float64).tofile(tmp + "/w.bin")
+    x.astype(np.float64).tofile(tmp + "/x.bin")
+    subprocess.check_call([O.REF_DRIVER, "mlp", "256", tmp + "/w.bin", tmp + "/x.bin", tmp + "/y.bin"],
+                          stdout=subprocess.DEVNULL)
+    y = np.fromfile(tmp + "/y.bin").reshape(4, 256).astype(np.float32)
+    np.savez_compressed(HERE + "/ponni_mlp_kat.npz", w=w, x=x, y=y)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
