@@ -1,0 +1,148 @@
+/* include/mw_b200.h -- C ABI of libmwb200.so, the B200 (sm_100a) implementation of miniWeatherML's
+ * time-stepping hot path.  Plain C: POD structs, raw pointers and sizes, integer status codes.
+ *
+ * The reference has no FFI for this path: its modules are header-only C++ classes the driver instantiates
+ * (experiments/supercell_example/driver.cpp:51-61).  The entry points below are what the host-side C++ module
+ * classes of this repo (miniweatherml_b200/host/) call, one per reference method they replace:
+ *
+ *   mw_dycore_create / _destroy           Dynamics_Euler_Stratified_WenoFV::init, dtor
+ *                                         (model/modules/dynamics_euler_stratified_wenofv.h:1197-1683)
+ *   mw_dycore_set_background              hy_dens_cells/_theta_cells/_edges/_theta_edges            (DYC:51-54,1325-1328)
+ *   mw_dycore_set_immersed                DataManager entry "immersed_proportion"                   (DYC:1313)
+ *   mw_dycore_compute_time_step           compute_time_step                                         (DYC:70-77)
+ *   mw_dycore_time_step[_host]            time_step(coupler, dt_phys)                               (DYC:81-198)
+ *   mw_dycore_init_supercell              init_supercell + convert_dynamics_to_coupler              (DYC:1687-1887,1891)
+ *   mw_kessler_step[_host]                Microphysics_Kessler::time_step                  (microphysics_kessler.h:99-162)
+ *   mw_surrogate_forward                  custom_modules::Microphysics_Kessler NN part (PON:177-202) + ponni
+ *                                         Inference::forward_batch_parallel (external/ponni/src/ponni_Inference.h:177)
+ *   mw_sponge_layer                       modules::sponge_layer                                 (sponge_layer.h:8-77)
+ *   mw_column_average / mw_nudge_to_column  ColumnNudger::set_column / nudge_to_column       (column_nudging.h:15-106)
+ *   mw_perturb_temperature                modules::perturb_temperature (thermal bubble)     (perturb_temperature.h:43-65)
+ *   mw_comm_*                             the MPI calls of halo_exchange / sponge / nudging, on NCCL
+ *
+ * Every function returns MW_OK (0) or a negative mw_status; mw_last_error() gives the message of the last
+ * failure on the calling thread (the C++ wrappers turn it into the reference's endrun() -> std::runtime_error).
+ * Unless a name ends in _host, all data pointers are DEVICE pointers owned by the caller (the DataManager), laid
+ * out exactly like the reference's arrays with nens == 1: [nz][ny][nx], x contiguous.  `stream` is a cudaStream_t
+ * passed as void* (NULL = default stream); calls are asynchronous on it unless stated otherwise.
+ */
+#ifndef MW_B200_H
+#define MW_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MW_MAX_TRACERS 8
+
+typedef enum {
+  MW_OK = 0,
+  MW_ERR_INVALID = -1,       /* bad argument / unsupported configuration (message says which) */
+  MW_ERR_CUDA = -2,          /* a CUDA runtime/driver call failed */
+  MW_ERR_NO_DEVICE = -3,     /* no sm_100 device visible: there is NO CPU fallback */
+  MW_ERR_NCCL = -4
+} mw_status;
+
+enum { MW_BC_PERIODIC = 0, MW_BC_OPEN = 1, MW_BC_WALL = 2 };       /* DYC:46-48 */
+
+/* Grid, decomposition and physics constants: the values the reference keeps in core::Coupler and its options. */
+typedef struct {
+  int    nx, ny, nz, nens;            /* local (per-rank) interior sizes; nens must be 1                          */
+  int    nx_glob, ny_glob;            /* global sizes (CPL:110); sim2d <=> ny_glob == 1                            */
+  int    i_beg, j_beg;                /* global index of local cell (0,0)  (CPL:147-153)                           */
+  int    nproc_x, nproc_y, px, py;    /* rank grid (CPL:127-145)                                                   */
+  double xlen, ylen, zlen;            /* domain size [m]; dx = xlen/nx_glob ... (CPL:316)                          */
+  int    num_tracers;                 /* <= MW_MAX_TRACERS                                                         */
+  int    idWV;                        /* tracer index of water vapour, -1 if none (DYC:1292)                       */
+  int    tracer_positive [MW_MAX_TRACERS];
+  int    tracer_adds_mass[MW_MAX_TRACERS];
+  double R_d, R_v, cp_d, p0, grav;    /* options set by micro/dycore init (KES:85-94, DYC:1227-1232)               */
+  double C0, gamma_d;                 /* DYC:1242-1247                                                             */
+  double earthrot, latitude;          /* fcor = 2*earthrot*sin(latitude) (DYC:213)                                 */
+  int    bc_x, bc_y, bc_z;            /* only periodic x/y are implemented; bc_z wall or open                      */
+  int    enable_gravity;
+  int    use_immersed_boundaries;
+} mw_config;
+
+typedef struct mw_dycore mw_dycore;   /* opaque: owns the haloed state buffers, flux scratch, TMA descriptors    */
+typedef struct mw_comm   mw_comm;     /* opaque: NCCL communicator + neighbour table + comm stream               */
+
+const char *mw_last_error(void);
+int  mw_version(void);
+/* 0 if a usable sm_100 device is present (selects nothing), MW_ERR_NO_DEVICE otherwise */
+int  mw_device_check(void);
+/* fills the derived constants (cv_d, gamma_d, kappa_d, C0) from R_d, cp_d, p0 exactly as DYC:1240-1247 */
+int  mw_config_defaults(mw_config *cfg);
+
+/* ---- dycore ------------------------------------------------------------------------------------------- */
+int  mw_dycore_create(const mw_config *cfg, mw_dycore **out);
+int  mw_dycore_destroy(mw_dycore *h);
+/* host pointers: hy_dens_cells[nz], hy_dens_theta_cells[nz], hy_dens_edges[nz+1], hy_dens_theta_edges[nz+1] */
+int  mw_dycore_set_background(mw_dycore *h, const double *hy_dens_cells, const double *hy_dens_theta_cells,
+                              const double *hy_dens_edges, const double *hy_dens_theta_edges);
+/* read them back (host pointers), e.g. to register "hy_dens_cells" in the DataManager (DYC:1663-1668) */
+int  mw_dycore_get_background(mw_dycore *h, double *hy_dens_cells, double *hy_dens_theta_cells,
+                              double *hy_dens_edges, double *hy_dens_theta_edges);
+int  mw_dycore_set_immersed(mw_dycore *h, const double *immersed_proportion /* device [nz][ny][nx] or NULL */);
+double mw_dycore_compute_time_step(const mw_dycore *h);
+/* fields: host array of 5+T DEVICE pointers in coupler order (density_dry,uvel,vvel,wvel,temp,tracers...) */
+int  mw_dycore_time_step(mw_dycore *h, double *const *fields, double dt_phys, void *stream);
+/* same through HOST buffers: H2D of the 5+T fields, the step, D2H of the results; synchronous */
+int  mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields, double dt_phys);
+/* supercell initial condition (hydrostatic GLL-quadrature column + cell averages) straight into coupler fields
+ * and into the handle's background profiles */
+int  mw_dycore_init_supercell(mw_dycore *h, double *const *fields, void *stream);
+/* attach a communicator: halos of decomposed directions then go through NCCL send/recv instead of a local wrap */
+int  mw_dycore_attach_comm(mw_dycore *h, mw_comm *comm);
+/* diagnostics: number of kernels this handle launched since creation */
+long long mw_dycore_launch_count(const mw_dycore *h);
+/* device time [ms] of the stage kernels / all kernels during the last time_step (CUDA events on the step's stream;
+ * valid after the stream has been synchronised); n_stage = stage-kernel launches inside that step */
+int  mw_dycore_last_timing(mw_dycore *h, float *stage_kernel_ms, int *n_stage, float *step_ms);
+int  mw_dycore_enable_timing(mw_dycore *h, int on);
+
+/* ---- WENO5 building block, exposed for the kernel-level parity tests ----------------------------------- */
+/* stencils: device [n][5]; out: device [n][2] (value at the low face, value at the high face)            */
+int  mw_weno5_edges(const double *stencils, double *out, long long n, void *stream);
+
+/* ---- Kessler microphysics ------------------------------------------------------------------------------ */
+/* device fields [nz][ncol]; precl device [ncol]; rainsplit_out (host int*, may be NULL) forces a sync when given.
+ * comm may be NULL (single rank); otherwise the sub-cycle count is min-reduced over ranks.                      */
+int  mw_kessler_step(int nz, long long ncol, double dz, double dt, double R_d, double R_v, double cp_d, double p0,
+                     double *temp, const double *rho_dry, double *rho_v, double *rho_c, double *rho_r,
+                     double *precl, mw_comm *comm, int *rainsplit_out, void *stream);
+int  mw_kessler_step_host(int nz, long long ncol, double dz, double dt, double R_d, double R_v, double cp_d,
+                          double p0, double *temp, const double *rho_dry, double *rho_v, double *rho_c,
+                          double *rho_r, double *precl, int *rainsplit_out);
+
+/* ---- ponni surrogate (5 -> 10 -> LeakyReLU(0.1) -> 4, fp32) ---------------------------------------------- */
+/* weights: HOST fp32 W1[5][10], b1[10], W2[10][4], b2[4]; scl_in HOST [5][2], scl_out HOST [4][2];
+ * in/out device fp64 [n].  use_tensor_cores != 0 selects the mma path (3xTF32 split), 0 the fp32 FMA path.   */
+int  mw_surrogate_forward(long long n, const float *weights, const double *scl_in, const double *scl_out,
+                          const double *temp, const double *rho_d, const double *rho_v, const double *rho_c,
+                          const double *rho_r, double *o_temp, double *o_rho_v, double *o_rho_c, double *o_rho_r,
+                          int use_tensor_cores, void *stream);
+/* the bare MLP on normalised fp32 inputs x[5][B] -> y[4][B] (device), for the ponni known-answer tests */
+int  mw_mlp_forward(long long B, const float *weights /*host*/, const float *x, float *y, int use_tensor_cores,
+                    void *stream);
+
+/* ---- the other calls of the canonical step loop ---------------------------------------------------------- */
+int  mw_sponge_layer(int nfields, double *const *fields, int nz, int ny, int nx, long long nx_glob_ny_glob,
+                     double dz, double zlen, double dt, double time_scale, mw_comm *comm, void *stream);
+/* column[5][nz] (device) <- horizontal mean of (density_dry,uvel,vvel,temp,water_vapor) */
+int  mw_column_average(const double *const *f5, int nz, int ny, int nx, long long nx_glob_ny_glob, double *column,
+                       mw_comm *comm, void *stream);
+int  mw_nudge_to_column(double *const *f5, int nz, int ny, int nx, long long nx_glob_ny_glob, double dt,
+                        const double *column, mw_comm *comm, void *stream);
+int  mw_perturb_temperature(double *temp, int nz, int ny, int nx, int i_beg, int j_beg, double dx, double dy,
+                            double dz, double xlen, double ylen, void *stream);
+
+/* ---- communicator (NCCL over NVLink), one process per GPU -------------------------------------------------- */
+int  mw_comm_unique_id(void *id_bytes_128);                       /* rank 0 creates, caller broadcasts            */
+int  mw_comm_create(const void *id_bytes_128, int nranks, int rank, mw_comm **out);
+int  mw_comm_destroy(mw_comm *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

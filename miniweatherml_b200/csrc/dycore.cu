@@ -1,0 +1,387 @@
+// Host side of the dycore C ABI (include/mw_b200.h): owns the device-resident RK registers, the tracer flux
+// scratch, the background profiles and the TMA descriptors, and sequences the kernels of one time_step
+// (reference: model/modules/dynamics_euler_stratified_wenofv.h:81-198).
+#include "dycore_kernels.cuh"
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <cstdlib>
+
+namespace mw {
+
+thread_local std::string g_last_error;
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+int device_check_cached() {
+  static int cached = 1;
+  if (cached == 1) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      set_error("no CUDA device visible (%s); libmwb200 has no CPU fallback", cudaGetErrorString(e));
+      cudaGetLastError();
+      return MW_ERR_NO_DEVICE;
+    }
+    int dev = 0, major = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) {
+      set_error("device compute capability %d.x, kernels are built for sm_100a only", major);
+      return MW_ERR_NO_DEVICE;
+    }
+    cached = MW_OK;
+  }
+  return cached;
+}
+
+int encode_tensor_map_f64_4d(CUtensorMap *map, const void *base, const uint64_t dims[4],
+                             const uint64_t strides_bytes[3], const uint32_t box[4]) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeTiled entry point not available (%s)", cudaGetErrorString(e));
+      return MW_ERR_CUDA;
+    }
+    fn = (encode_fn) p;
+  }
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), (const cuuint64_t *) dims,
+                  (const cuuint64_t *) strides_bytes, (const cuuint32_t *) box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int) r);
+    return MW_ERR_CUDA;
+  }
+  return MW_OK;
+}
+
+}  // namespace mw
+
+using namespace mw;
+
+// tile of columns one CTA owns; two threads per column
+constexpr int TILE_X = 32, TILE_Y = 8;
+
+struct mw_dycore {
+  mw_config cfg;
+  int N;
+  double dx, dy, dz;
+  int pitch;
+  long long zstride, vstride;
+  size_t qbytes;
+  double *q[3] = {nullptr, nullptr, nullptr};
+  CUtensorMap tmap[3];
+  double *flux_x = nullptr, *flux_y = nullptr, *flux_z = nullptr, *mult = nullptr;
+  double *bg = nullptr;                // hyc[nz], hytc[nz], hye[nz+1], hyte[nz+1]
+  std::vector<double> bg_host;
+  bool bg_set = false;
+  const double *immersed = nullptr;
+  mw_comm *comm = nullptr;
+  long long launches = 0;
+  int use_tma = 1;
+  // staging for the *_host entry point
+  double *dev_fields[NUM_STATE + MW_MAX_TRACERS] = {nullptr};
+  bool dev_fields_alloc = false;
+  // timing
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;         // [0]=step begin, [1]=step end, then pairs per stage kernel
+  int n_stage_timed = 0;
+};
+
+static StageParams base_params(const mw_dycore *h) {
+  StageParams P;
+  memset(&P, 0, sizeof(P));
+  const mw_config &c = h->cfg;
+  P.nx = c.nx; P.ny = c.ny; P.nz = c.nz;
+  P.pitch = h->pitch; P.zstride = h->zstride; P.vstride = h->vstride;
+  P.flux_x = h->flux_x; P.flux_y = h->flux_y; P.flux_z = h->flux_z; P.mult = h->mult;
+  P.hyc = h->bg; P.hytc = h->bg + c.nz; P.hye = h->bg + 2 * c.nz; P.hyte = h->bg + 2 * c.nz + (c.nz + 1);
+  P.immersed = h->immersed;
+  P.dx = h->dx; P.dy = h->dy; P.dz = h->dz;
+  P.rdx = 1.0 / h->dx; P.rdy = 1.0 / h->dy; P.rdz = 1.0 / h->dz;
+  P.C0 = c.C0; P.gamma = c.gamma_d; P.grav = c.grav;
+  P.fcor = 2 * c.earthrot * sin(c.latitude);
+  P.sim2d = (c.ny_glob == 1);
+  P.bc_z = c.bc_z;
+  P.enable_gravity = c.enable_gravity;
+  P.use_immersed = (c.use_immersed_boundaries && h->immersed) ? 1 : 0;
+  P.wrap_x = (c.nproc_x == 1);
+  P.wrap_y = (c.nproc_y == 1) && !P.sim2d;
+  unsigned pm = 0;
+  for (int t = 0; t < c.num_tracers; ++t) if (c.tracer_positive[t]) pm |= 1u << t;
+  P.positive_mask = pm;
+  P.use_tma = h->use_tma;
+  return P;
+}
+
+extern "C" const char *mw_last_error(void) { return g_last_error.c_str(); }
+extern "C" int mw_version(void) { return 100; }
+extern "C" int mw_device_check(void) { return device_check_cached(); }
+
+extern "C" int mw_config_defaults(mw_config *cfg) {
+  MW_REQUIRE(cfg, "mw_config_defaults: null config");
+  if (cfg->R_d == 0) cfg->R_d = 287.;
+  if (cfg->cp_d == 0) cfg->cp_d = 1003.;
+  if (cfg->R_v == 0) cfg->R_v = 461.;
+  if (cfg->p0 == 0) cfg->p0 = 1.e5;
+  if (cfg->grav == 0) cfg->grav = 9.81;
+  if (cfg->earthrot == 0) cfg->earthrot = 7.292115e-5;
+  const double cv_d = cfg->cp_d - cfg->R_d;                                 // DYC:1240-1247
+  cfg->gamma_d = cfg->cp_d / cv_d;
+  const double kappa_d = cfg->R_d / cfg->cp_d;
+  cfg->C0 = pow(cfg->R_d * pow(cfg->p0, -kappa_d), cfg->gamma_d);
+  return MW_OK;
+}
+
+extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
+  MW_REQUIRE(cfg && out, "mw_dycore_create: null argument");
+  int rc = device_check_cached();
+  if (rc != MW_OK) return rc;
+  MW_REQUIRE(cfg->nens == 1, "nens = %d: only nens == 1 is implemented", cfg->nens);
+  MW_REQUIRE(cfg->nx >= HALO && cfg->nz >= 2 && cfg->ny >= 1, "grid too small (nx=%d ny=%d nz=%d)", cfg->nx, cfg->ny, cfg->nz);
+  MW_REQUIRE(cfg->ny_glob == 1 || cfg->ny >= HALO, "ny = %d too small for a 3-D run", cfg->ny);
+  MW_REQUIRE(cfg->num_tracers >= 0 && cfg->num_tracers <= MW_MAX_TRACERS, "num_tracers = %d out of range", cfg->num_tracers);
+  MW_REQUIRE(cfg->num_tracers <= 4, "num_tracers = %d: stage kernel is instantiated for 0..4 tracers", cfg->num_tracers);
+  MW_REQUIRE(cfg->bc_x == MW_BC_PERIODIC && cfg->bc_y == MW_BC_PERIODIC, "only periodic bc_x/bc_y are implemented");
+  MW_REQUIRE(cfg->bc_z == MW_BC_WALL || cfg->bc_z == MW_BC_OPEN, "bc_z must be wall or open");
+  MW_REQUIRE(cfg->C0 > 0 && cfg->gamma_d > 1, "C0/gamma_d not set (call mw_config_defaults)");
+  mw_dycore *h = new mw_dycore();
+  h->cfg = *cfg;
+  h->N = NUM_STATE + cfg->num_tracers;
+  h->dx = cfg->xlen / cfg->nx_glob; h->dy = cfg->ylen / cfg->ny_glob; h->dz = cfg->zlen / cfg->nz;
+  h->pitch = ((cfg->nx + 2 * HALO + 1) / 2) * 2;
+  h->zstride = (long long) (cfg->ny + 2 * HALO) * h->pitch;
+  h->vstride = (long long) cfg->nz * h->zstride;
+  h->qbytes = (size_t) h->N * h->vstride * sizeof(double);
+  const char *e = getenv("MW_NO_TMA");
+  h->use_tma = (e && atoi(e) != 0) ? 0 : 1;
+  const int T = cfg->num_tracers > 0 ? cfg->num_tracers : 1;
+  const size_t nzl = cfg->nz, nyl = cfg->ny, nxl = cfg->nx;
+  cudaError_t ce = cudaSuccess;
+  for (int b = 0; b < 3 && ce == cudaSuccess; ++b) {
+    ce = cudaMalloc(&h->q[b], h->qbytes);
+    if (ce == cudaSuccess) ce = cudaMemset(h->q[b], 0, h->qbytes);
+  }
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->flux_x, T * nzl * nyl * (nxl + 1) * 8);
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->flux_y, T * nzl * (nyl + 1) * nxl * 8);
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->flux_z, T * (nzl + 1) * nyl * nxl * 8);
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->mult, T * nzl * nyl * nxl * 8);
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->bg, (4 * nzl + 2) * 8);
+  if (ce != cudaSuccess) {
+    set_error("mw_dycore_create: device allocation failed: %s", cudaGetErrorString(ce));
+    mw_dycore_destroy(h);
+    return MW_ERR_CUDA;
+  }
+  for (int b = 0; b < 3; ++b) {
+    const uint64_t dims[4] = {(uint64_t) h->pitch, (uint64_t) (cfg->ny + 2 * HALO), (uint64_t) cfg->nz, (uint64_t) h->N};
+    const uint64_t str[3] = {(uint64_t) h->pitch * 8, (uint64_t) h->zstride * 8, (uint64_t) h->vstride * 8};
+    const uint32_t box[4] = {TILE_X + 2 * HALO, TILE_Y + 2 * HALO, 1, (uint32_t) h->N};
+    rc = encode_tensor_map_f64_4d(&h->tmap[b], h->q[b], dims, str, box);
+    if (rc != MW_OK) { mw_dycore_destroy(h); return rc; }
+  }
+  *out = h;
+  return MW_OK;
+}
+
+extern "C" int mw_dycore_destroy(mw_dycore *h) {
+  if (!h) return MW_OK;
+  for (int b = 0; b < 3; ++b) cudaFree(h->q[b]);
+  cudaFree(h->flux_x); cudaFree(h->flux_y); cudaFree(h->flux_z); cudaFree(h->mult); cudaFree(h->bg);
+  if (h->dev_fields_alloc) for (int f = 0; f < h->N; ++f) cudaFree(h->dev_fields[f]);
+  for (auto e : h->ev) cudaEventDestroy(e);
+  delete h;
+  return MW_OK;
+}
+
+extern "C" int mw_dycore_set_background(mw_dycore *h, const double *hyc, const double *hytc, const double *hye,
+                                        const double *hyte) {
+  MW_REQUIRE(h && hyc && hytc && hye && hyte, "mw_dycore_set_background: null argument");
+  const int nz = h->cfg.nz;
+  h->bg_host.resize(4 * nz + 2);
+  memcpy(&h->bg_host[0], hyc, nz * 8);
+  memcpy(&h->bg_host[nz], hytc, nz * 8);
+  memcpy(&h->bg_host[2 * nz], hye, (nz + 1) * 8);
+  memcpy(&h->bg_host[3 * nz + 1], hyte, (nz + 1) * 8);
+  MW_CUDA_OK(cudaMemcpy(h->bg, h->bg_host.data(), h->bg_host.size() * 8, cudaMemcpyHostToDevice));
+  h->bg_set = true;
+  return MW_OK;
+}
+
+extern "C" int mw_dycore_get_background(mw_dycore *h, double *hyc, double *hytc, double *hye, double *hyte) {
+  MW_REQUIRE(h && h->bg_set, "mw_dycore_get_background: background not set");
+  const int nz = h->cfg.nz;
+  if (hyc) memcpy(hyc, &h->bg_host[0], nz * 8);
+  if (hytc) memcpy(hytc, &h->bg_host[nz], nz * 8);
+  if (hye) memcpy(hye, &h->bg_host[2 * nz], (nz + 1) * 8);
+  if (hyte) memcpy(hyte, &h->bg_host[3 * nz + 1], (nz + 1) * 8);
+  return MW_OK;
+}
+
+extern "C" int mw_dycore_set_immersed(mw_dycore *h, const double *immersed) {
+  MW_REQUIRE(h, "mw_dycore_set_immersed: null handle");
+  h->immersed = immersed;
+  return MW_OK;
+}
+
+extern "C" double mw_dycore_compute_time_step(const mw_dycore *h) {      // DYC:70-77
+  if (!h) return 0.0;
+  const double maxwave = 350 + 80, cfl = 0.6;
+  return cfl * fmin(fmin(h->dx, h->dy), h->dz) / maxwave;
+}
+
+extern "C" long long mw_dycore_launch_count(const mw_dycore *h) { return h ? h->launches : 0; }
+
+extern "C" int mw_dycore_enable_timing(mw_dycore *h, int on) {
+  MW_REQUIRE(h, "null handle");
+  h->timing = on != 0;
+  return MW_OK;
+}
+
+extern "C" int mw_dycore_last_timing(mw_dycore *h, float *stage_ms, int *n_stage, float *step_ms) {
+  MW_REQUIRE(h && h->timing && h->ev.size() >= 2, "timing not enabled or no step taken");
+  float s = 0, t = 0;
+  MW_CUDA_OK(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+  for (int i = 0; i < h->n_stage_timed; ++i) {
+    float d = 0;
+    MW_CUDA_OK(cudaEventElapsedTime(&d, h->ev[2 + 2 * i], h->ev[3 + 2 * i]));
+    s += d;
+  }
+  if (stage_ms) *stage_ms = s;
+  if (n_stage) *n_stage = h->n_stage_timed;
+  if (step_ms) *step_ms = t;
+  return MW_OK;
+}
+
+template <int NT>
+static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
+  using C = StageCfg<NT, TILE_X, TILE_Y>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MW_CUDA_OK(cudaFuncSetAttribute(k_stage<NT, TILE_X, TILE_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int) C::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((P.nx + TILE_X - 1) / TILE_X, (P.ny + TILE_Y - 1) / TILE_Y);
+  k_stage<NT, TILE_X, TILE_Y><<<grid, C::NTHR, C::SMEM_BYTES, st>>>(h->tmap[in_buf], P);
+  MW_CUDA_OK(cudaGetLastError());
+  h->launches++;
+  if (NT > 0) {
+    const long long ncell = (long long) P.nz * P.ny * P.nx;
+    k_tracer_update<NT><<<(unsigned) ((ncell + 255) / 256), 256, 0, st>>>(P);
+    MW_CUDA_OK(cudaGetLastError());
+    h->launches++;
+  }
+  return MW_OK;
+}
+
+template <int NT>
+static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaStream_t st) {
+  const mw_config &c = h->cfg;
+  const long long ncell = (long long) c.nz * c.ny * c.nx;
+  const unsigned cgrid = (unsigned) ((ncell + 255) / 256);
+  ConvertParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.S = base_params(h);
+  for (int f = 0; f < h->N; ++f) Q.fields[f] = fields[f];
+  Q.R_d = c.R_d; Q.R_v = c.R_v; Q.idWV = c.idWV;
+  unsigned am = 0;
+  for (int t = 0; t < c.num_tracers; ++t) if (c.tracer_adds_mass[t]) am |= 1u << t;
+  Q.adds_mass_mask = am;
+
+  auto ensure_events = [&](size_t n) {
+    while (h->ev.size() < n) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
+  };
+  h->n_stage_timed = 0;
+  if (h->timing) { ensure_events(2); cudaEventRecord(h->ev[0], st); }
+
+  Q.S.qout = h->q[0];
+  k_coupler_to_dyn<NT><<<cgrid, 256, 0, st>>>(Q);
+  MW_CUDA_OK(cudaGetLastError());
+  h->launches++;
+
+  double dt_dyn = mw_dycore_compute_time_step(h);
+  const int ncycles = (int) ceil(dt_phys / dt_dyn);                        // DYC:104-108
+  dt_dyn = dt_phys / ncycles;
+  for (int ic = 0; ic < ncycles; ++ic) {
+    for (int s = 0; s < 3; ++s) {
+      StageParams P = base_params(h);
+      int in_buf;
+      if (s == 0)      { in_buf = 0; P.qout = h->q[1]; P.rk_a = 0.0;     P.rk_b = 1.0;     P.rk_cdt = dt_dyn;               P.dt_stage = dt_dyn; }
+      else if (s == 1) { in_buf = 1; P.qout = h->q[2]; P.rk_a = 3. / 4.; P.rk_b = 1. / 4.; P.rk_cdt = (1. / 4.) * dt_dyn;   P.dt_stage = (1. / 4.) * dt_dyn; }
+      else             { in_buf = 2; P.qout = h->q[0]; P.rk_a = 1. / 3.; P.rk_b = 2. / 3.; P.rk_cdt = (2. / 3.) * dt_dyn;   P.dt_stage = (2. / 3.) * dt_dyn; }
+      P.qin = h->q[in_buf];
+      P.q0 = h->q[0];
+      if (h->timing) { ensure_events(4 + 2 * h->n_stage_timed); cudaEventRecord(h->ev[2 + 2 * h->n_stage_timed], st); }
+      int rc = launch_stage<NT>(h, P, in_buf, st);
+      if (rc != MW_OK) return rc;
+      if (h->timing) { cudaEventRecord(h->ev[3 + 2 * h->n_stage_timed], st); h->n_stage_timed++; }
+    }
+  }
+  Q.S.qin = h->q[0];
+  k_dyn_to_coupler<NT><<<cgrid, 256, 0, st>>>(Q);
+  MW_CUDA_OK(cudaGetLastError());
+  h->launches++;
+  if (h->timing) cudaEventRecord(h->ev[1], st);
+  return MW_OK;
+}
+
+extern "C" int mw_dycore_time_step(mw_dycore *h, double *const *fields, double dt_phys, void *stream) {
+  MW_REQUIRE(h && fields, "mw_dycore_time_step: null argument");
+  MW_REQUIRE(h->bg_set, "mw_dycore_time_step: background profiles not set");
+  MW_REQUIRE(dt_phys > 0, "mw_dycore_time_step: dt_phys = %g", dt_phys);
+  MW_REQUIRE(h->cfg.nproc_x * h->cfg.nproc_y == 1 || h->comm, "decomposed run without an attached communicator");
+  cudaStream_t st = (cudaStream_t) stream;
+  switch (h->cfg.num_tracers) {
+    case 0: return step_impl<0>(h, fields, dt_phys, st);
+    case 1: return step_impl<1>(h, fields, dt_phys, st);
+    case 2: return step_impl<2>(h, fields, dt_phys, st);
+    case 3: return step_impl<3>(h, fields, dt_phys, st);
+    case 4: return step_impl<4>(h, fields, dt_phys, st);
+  }
+  set_error("unsupported num_tracers");
+  return MW_ERR_INVALID;
+}
+
+extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields, double dt_phys) {
+  MW_REQUIRE(h && host_fields, "mw_dycore_time_step_host: null argument");
+  const size_t bytes = (size_t) h->cfg.nz * h->cfg.ny * h->cfg.nx * 8;
+  if (!h->dev_fields_alloc) {
+    for (int f = 0; f < h->N; ++f) MW_CUDA_OK(cudaMalloc(&h->dev_fields[f], bytes));
+    h->dev_fields_alloc = true;
+  }
+  for (int f = 0; f < h->N; ++f) MW_CUDA_OK(cudaMemcpyAsync(h->dev_fields[f], host_fields[f], bytes, cudaMemcpyHostToDevice, 0));
+  int rc = mw_dycore_time_step(h, h->dev_fields, dt_phys, nullptr);
+  if (rc != MW_OK) return rc;
+  for (int f = 0; f < h->N; ++f) MW_CUDA_OK(cudaMemcpyAsync(host_fields[f], h->dev_fields[f], bytes, cudaMemcpyDeviceToHost, 0));
+  MW_CUDA_OK(cudaStreamSynchronize(0));
+  return MW_OK;
+}
+
+extern "C" int mw_dycore_attach_comm(mw_dycore *h, mw_comm *comm) {
+  MW_REQUIRE(h, "null handle");
+  h->comm = comm;
+  return MW_OK;
+}
+
+extern "C" int mw_weno5_edges(const double *stencils, double *out, long long n, void *stream) {
+  int rc = device_check_cached();
+  if (rc != MW_OK) return rc;
+  MW_REQUIRE(stencils && out && n >= 0, "mw_weno5_edges: bad argument");
+  if (n == 0) return MW_OK;
+  k_weno5_edges<<<(unsigned) ((n + 255) / 256), 256, 0, (cudaStream_t) stream>>>(stencils, out, n);
+  MW_CUDA_OK(cudaGetLastError());
+  return MW_OK;
+}

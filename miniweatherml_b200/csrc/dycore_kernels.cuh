@@ -1,0 +1,625 @@
+// Device side of the dycore: the fused SSPRK3 stage kernel and its small companions.
+//
+// Data layout in HBM ("dycore form", one buffer per RK register q0/q1/q2):
+//     qd[l][k][jh][ih]   l = 0..N-1 (rho', u, v, w, (rho*theta)', tracer concentrations c = rho_tr/rho)
+//                        k = 0..nz-1 (no z halo: the z boundary condition is applied in-kernel)
+//                        jh = j+3, ih = i+3   halo of 3 cells in x and y, row pitch padded to an even count
+// i.e. the *divided* variables the reference reconstructs (DYC:248-255) are what is stored; conserved values
+// are re-formed (u*rho) where the RK combination needs them, exactly like the reference's multiply-back
+// (DYC:477-484).  A halo of 3 (reference: 2 + edge_exchange) lets a tile reconstruct its ring cells itself,
+// which removes the second exchange per stage (DYC:830-1082).
+#pragma once
+#include "mw_common.cuh"
+
+namespace mw {
+
+constexpr int HALO = 3;
+enum { idR = 0, idU = 1, idV = 2, idW = 3, idT = 4, NUM_STATE = 5 };
+
+struct StageParams {
+  int nx, ny, nz;
+  int pitch;                 // row pitch of the haloed arrays (doubles)
+  long long zstride;         // (ny+6)*pitch
+  long long vstride;         // nz*zstride
+  const double *qin;         // stage input  (dycore form, haloed)
+  const double *q0;          // RK register q0 (dycore form, haloed); unused when rk_a == 0
+  double *qout;              // stage output (dycore form, haloed); may alias q0 (stage 3)
+  double *flux_x, *flux_y, *flux_z;   // tracer face fluxes [T][nz][ny][nx+1], [T][nz][ny+1][nx], [T][nz+1][ny][nx]
+  double *mult;              // FCT scaling factor per tracer cell [T][nz][ny][nx]
+  const double *hyc, *hytc, *hye, *hyte;   // background profiles (device)
+  const double *immersed;    // [nz][ny][nx] or nullptr
+  double rdx, rdy, rdz, dx, dy, dz;
+  double C0, gamma, grav, fcor;
+  double rk_a, rk_b, rk_cdt; // q_new = rk_a*q0 + rk_b*q + rk_cdt*L(q)
+  double dt_stage;           // the dt handed to compute_tendencies (FCT and immersed time scale), DYC:119,136,157
+  int sim2d, bc_z, enable_gravity, use_immersed;
+  int wrap_x, wrap_y;        // write periodic images into the halo (single rank in that direction)
+  int lo_x_seam, hi_x_seam, lo_y_seam, hi_y_seam;   // local face 0 / nx (ny) lies on the global periodic seam
+  unsigned positive_mask;    // bit tr set <=> tracer tr must stay non-negative
+  int use_tma;
+};
+
+// --------------------------------------------------------------------------------------------------------
+// small helpers
+// --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_with_images(double *var_base, const StageParams &P, int k, int j, int i,
+                                                  double v) {
+  double *row = var_base + (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + HALO;
+  row[i] = v;
+  if (P.wrap_x) {
+    if (i < HALO) row[i + P.nx] = v;
+    if (i >= P.nx - HALO) row[i - P.nx] = v;
+  }
+  if (P.wrap_y) {
+    if (j < HALO) row[i + (long long) P.ny * P.pitch] = v;
+    if (j >= P.ny - HALO) row[i - (long long) P.ny * P.pitch] = v;
+  }
+}
+
+// p = C0 * rt^gamma  (DYC:401)
+__device__ __forceinline__ double eos_pressure(double rt, double C0, double gamma) { return C0 * pow(rt, gamma); }
+
+// Acoustic upwind of pressure and normal mass flux (DYC:398-408): returns m*, p* and which side is upwind.
+__device__ __forceinline__ void riemann(double pL, double pR, double mL, double mR, double &m_upw, double &p_upw,
+                                        bool &up_is_L) {
+  constexpr double cs = 350.0;
+  const double w1 = 0.5 * (pR - cs * mR), w2 = 0.5 * (pL + cs * mL);
+  p_upw = w1 + w2;
+  m_upw = (w2 - w1) * (1.0 / cs);
+  up_is_L = (mL + mR > 0.0);
+}
+
+// Work distribution inside a CTA: warps fetch chunks of 32 jobs from a shared counter, so phases that mix
+// long jobs (a reconstruction + two pows) with short ones balance themselves.
+template <class F>
+__device__ __forceinline__ void run_jobs(int *ctr, int total, F &&f) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(ctr, 32);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= total) break;
+    const int idx = base + lane;
+    if (idx < total) f(idx);
+  }
+}
+
+template <int NT, int TX_, int TY_>
+struct StageCfg {
+  static constexpr int N = NUM_STATE + NT;
+  static constexpr int TX = TX_, TY = TY_;
+  static constexpr int TT = TX * TY;                       // owned cells per level
+  static constexpr int NTHR = 2 * TT;                      // two threads per owned column
+  static constexpr int NH = (N + 1) / 2;                   // variables per z-owner thread
+  static constexpr int PX = TX + 2 * HALO, PY = TY + 2 * HALO, PLANE = PX * PY;
+  static constexpr int SLOT = N * PLANE;                   // doubles per haloed plane of all variables
+  static constexpr int SLOTP = ((SLOT + 15) / 16) * 16;    // slot stride: TMA destinations stay 128-byte aligned
+  static constexpr int XC = TY * (TX + 2);                 // cells reconstructed in x per level (with ring)
+  static constexpr int YC = (TY + 2) * TX;                 // cells reconstructed in y per level (with ring)
+  static constexpr int XF = TY * (TX + 1);                 // x faces per level
+  static constexpr int YF = (TY + 1) * TX;                 // y faces per level
+  static constexpr int OFF_W = 0;                          // two plane slots
+  static constexpr int OFF_EX = OFF_W + 2 * SLOTP;          // [N+1][2][XC]  edge values, variable N = pressure
+  static constexpr int OFF_EY = OFF_EX + (N + 1) * 2 * XC; // [N+1][2][YC]
+  static constexpr int OFF_Z = OFF_EY + (N + 1) * 2 * YC;  // rho/w/p edge values of the z face: [3][2][TT]
+  static constexpr int OFF_FX = OFF_Z + 6 * TT;            // [N][XF]
+  static constexpr int OFF_FY = OFF_FX + N * XF;           // [N][YF]
+  static constexpr int OFF_END = OFF_FY + N * YF;
+  static constexpr size_t SMEM_BYTES = (size_t) OFF_END * 8 + 128;   // + 2 mbarriers and 4 job counters
+};
+
+// --------------------------------------------------------------------------------------------------------
+// The stage kernel: one CTA owns a TX x TY tile of columns and marches over all levels.
+// Two threads share each owned column ("owners"): each keeps a five-level register window of half the variables.
+// Per level k (three CTA barriers):
+//   A  owners reconstruct level k+1 in z from their window (k-1..k+3) and publish the rho/w/p edge values of
+//      face k+1/2; then all warps pull x- and y-reconstruction jobs of level k (tile + 1-cell ring) from a
+//      shared counter; the (rho*theta)' jobs also evaluate the two edge pressures
+//   B  x- and y-face jobs (acoustic upwind p*, m*; advective upwind of everything else) into smem, tracer face
+//      fluxes to HBM; owners do the same for the z face k+1/2 with their own variables
+//   C  owners form the tendency of their variables in cell (k, y, x), add gravity/Coriolis/immersed forcing,
+//      apply the RK combination and store the new state (state variables) or, for tracers, the RK base value
+//      and the FCT factor that k_tracer_update finishes with.
+// The plane of level k+2 arrives by TMA into the slot plane k just vacated while B and C run.
+// --------------------------------------------------------------------------------------------------------
+template <int NT, int TX, int TY>
+__global__ void __launch_bounds__(2 * TX * TY, 1)
+k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
+  using C = StageCfg<NT, TX, TY>;
+  constexpr int N = C::N, NH = C::NH, TT = C::TT, PX = C::PX, PLANE = C::PLANE, NTHR = C::NTHR;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double *sm = reinterpret_cast<double *>(smem_raw);
+  double *W = sm + C::OFF_W;
+  double *Ex = sm + C::OFF_EX;
+  double *Ey = sm + C::OFF_EY;
+  double *Zs = sm + C::OFF_Z;
+  double *Fx = sm + C::OFF_FX;
+  double *Fy = sm + C::OFF_FY;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sm + C::OFF_END);   // 2 mbarriers
+  int *ctr = reinterpret_cast<int *>(bar + 2);                      // [2 parities][2 phases]
+
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+  const int nz = P.nz;
+  const bool wall = (P.bc_z == MW_BC_WALL);
+  const bool use_tma = P.use_tma != 0;
+
+  // owner identity: column (oy, ox) and variable half
+  const int oc = tid % TT, oh = tid / TT;
+  const int oy = oc / TX, ox = oc % TX;
+  const int v0 = oh * NH;                                  // first owned variable
+  const int gi = i0 + ox, gj = j0 + oy;
+  const bool in_dom = (gi < P.nx) && (gj < P.ny);
+  // column base in the haloed global arrays (clamped inside the domain for overhanging tiles)
+  const long long colbase = (long long) (min(gj, P.ny - 1) + HALO) * P.pitch + (min(gi, P.nx - 1) + HALO);
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+    if (use_tma) tma_prefetch_desc(&tmap);
+    ctr[0] = ctr[1] = ctr[2] = ctr[3] = 0;
+  }
+  __syncthreads();
+
+#define MW_LOAD_PLANE(lev)                                                                                     \
+  do {                                                                                                         \
+    double *dst__ = W + ((lev) & 1) * C::SLOTP;                                                                 \
+    if (use_tma) {                                                                                             \
+      if (tid == 0) {                                                                                          \
+        fence_proxy_async();                                                                                   \
+        mbar_expect_tx(&bar[(lev) & 1], (uint32_t) (C::SLOT * 8));                                             \
+        tma_load_4d(dst__, &tmap, &bar[(lev) & 1], i0, j0, (lev), 0);                                          \
+      }                                                                                                        \
+    } else {                                                                                                   \
+      for (int idx__ = tid; idx__ < C::SLOT; idx__ += NTHR) {                                                  \
+        const int l__ = idx__ / PLANE, c__ = idx__ % PLANE, jh__ = j0 + c__ / PX, ih__ = i0 + c__ % PX;        \
+        double v__ = 0.0;                                                                                      \
+        if (jh__ < P.ny + 2 * HALO && ih__ < P.pitch)                                                          \
+          v__ = P.qin[(long long) l__ * P.vstride + (long long) (lev) * P.zstride + (long long) jh__ * P.pitch + ih__]; \
+        dst__[idx__] = v__;                                                                                    \
+      }                                                                                                        \
+    }                                                                                                          \
+  } while (0)
+
+  // value of variable l at level lev of my column with the z boundary condition applied (DYC:752-781):
+  // wall/open copy the nearest interior cell, wall zeroes w.
+#define MW_ZLOAD(l, lev)                                                                                       \
+  ([&]() -> double {                                                                                           \
+    const int lv__ = (lev);                                                                                    \
+    const int lc__ = lv__ < 0 ? 0 : (lv__ >= nz ? nz - 1 : lv__);                                              \
+    double v__ = __ldg(P.qin + (long long) (l) * P.vstride + (long long) lc__ * P.zstride + colbase);          \
+    if ((l) == idW && wall && lc__ != lv__) v__ = 0.0;                                                         \
+    return v__;                                                                                                \
+  }())
+
+  double win[NH][5];      // levels c-2 .. c+2 around the level c reconstructed next
+  double nxt[NH];         // level c+3
+  double vhi_prev[NH];    // high-edge value of the previously reconstructed level (L state of the next face)
+  double p_hi_prev;       // its pressure (meaningful for the owner of idT only)
+  double fz_lo[NH];       // flux of my variables through the low z face of the current level
+  double zm_lo;           // mass flux through the low z face of the current level
+#pragma unroll
+  for (int v = 0; v < NH; ++v) {
+    const int l = v0 + v;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) win[v][s] = (l < N) ? MW_ZLOAD(l, s - 2) : 0.0;
+    nxt[v] = (l < N) ? MW_ZLOAD(l, 3) : 0.0;
+  }
+
+  MW_LOAD_PLANE(0);
+  if (nz > 1) MW_LOAD_PLANE(1);
+
+  double vlo[NH], vhi[NH], p_lo = 0.0, p_hi = 0.0;
+  // reconstruct the level the window is centred on (kz); pressures at its two faces for the idT owner
+#define MW_Z_RECON(kz)                                                                                         \
+  _Pragma("unroll") for (int v = 0; v < NH; ++v) {                                                             \
+    const int l = v0 + v;                                                                                      \
+    if (l < N) {                                                                                               \
+      weno5_edges(win[v][0], win[v][1], win[v][2], win[v][3], win[v][4], vlo[v], vhi[v]);                      \
+      if (l == idT) {                                                                                          \
+        p_lo = eos_pressure(vlo[v] + __ldg(P.hyte + (kz)), P.C0, P.gamma);                                     \
+        p_hi = eos_pressure(vhi[v] + __ldg(P.hyte + (kz) + 1), P.C0, P.gamma);                                 \
+      }                                                                                                        \
+    } else { vlo[v] = 0.0; vhi[v] = 0.0; }                                                                     \
+  }
+  // publish the Riemann inputs of a z face: Zs[q][side][TT], q: 0 full density, 1 w, 2 pressure
+#define MW_Z_PUBLISH(L, R, pL, pR, face)                                                                       \
+  _Pragma("unroll") for (int v = 0; v < NH; ++v) {                                                             \
+    const int l = v0 + v;                                                                                      \
+    if (l == idR) {                                                                                            \
+      const double he = __ldg(P.hye + (face));                                                                 \
+      Zs[0 * TT + oc] = L[v] + he; Zs[1 * TT + oc] = R[v] + he;                                                \
+    } else if (l == idW) {                                                                                     \
+      Zs[2 * TT + oc] = L[v]; Zs[3 * TT + oc] = R[v];                                                          \
+    } else if (l == idT) {                                                                                     \
+      Zs[4 * TT + oc] = (pL); Zs[5 * TT + oc] = (pR);                                                          \
+    }                                                                                                          \
+  }
+  // z face flux of my variables (DYC:453-474); every owner recomputes the cheap Riemann part
+#define MW_Z_FLUX(L, R, face, fz, zm)                                                                          \
+  do {                                                                                                         \
+    const double rL = Zs[0 * TT + oc], rR = Zs[1 * TT + oc];                                                   \
+    const double mL = Zs[2 * TT + oc] * rL, mR = Zs[3 * TT + oc] * rR;                                         \
+    double m_upw, p_upw; bool upL;                                                                             \
+    riemann(Zs[4 * TT + oc], Zs[5 * TT + oc], mL, mR, m_upw, p_upw, upL);                                      \
+    const double r_up = upL ? rL : rR;                                                                         \
+    zm = m_upw;                                                                                                \
+    _Pragma("unroll") for (int v = 0; v < NH; ++v) {                                                           \
+      const int l = v0 + v;                                                                                    \
+      if (l < N) {                                                                                             \
+        const double q_up = upL ? L[v] : R[v];                                                                 \
+        double f;                                                                                              \
+        if (l == idR) f = m_upw;                                                                               \
+        else if (l == idT) f = m_upw * (q_up + __ldg(P.hyte + (face))) * fast_rcp(r_up);                       \
+        else f = m_upw * q_up;                                                                                 \
+        if (l == idW) f += p_upw;                                                                              \
+        fz[v] = f;                                                                                             \
+        if (l >= NUM_STATE && in_dom)                                                                          \
+          P.flux_z[((long long) (l - NUM_STATE) * (nz + 1) + (face)) * ((long long) P.ny * P.nx) +             \
+                   (long long) gj * P.nx + gi] = f;                                                            \
+      } else fz[v] = 0.0;                                                                                      \
+    }                                                                                                          \
+  } while (0)
+  // shift the window up one level; afterwards it is centred on c+1 and nxt holds level c+4
+#define MW_Z_ADVANCE(c)                                                                                        \
+  _Pragma("unroll") for (int v = 0; v < NH; ++v) {                                                             \
+    _Pragma("unroll") for (int s = 0; s < 4; ++s) win[v][s] = win[v][s + 1];                                   \
+    win[v][4] = nxt[v];                                                                                        \
+    const int l = v0 + v;                                                                                      \
+    nxt[v] = (l < N) ? MW_ZLOAD(l, (c) + 4) : 0.0;                                                             \
+  }
+
+  // ---- prologue: reconstruct level 0 and the bottom boundary face -----------------------------------------
+  MW_Z_RECON(0);
+  {
+    double Lb[NH], Rb[NH];
+#pragma unroll
+    for (int v = 0; v < NH; ++v) {
+      const int l = v0 + v;
+      Rb[v] = vlo[v];
+      if (l == idW && wall) Rb[v] = 0.0;
+      Lb[v] = Rb[v];                                      // DYC:1020-1038: both sides mirrored from the interior
+    }
+    MW_Z_PUBLISH(Lb, Rb, p_lo, p_lo, 0);
+    __syncthreads();
+    MW_Z_FLUX(Lb, Rb, 0, fz_lo, zm_lo);
+#pragma unroll
+    for (int v = 0; v < NH; ++v) vhi_prev[v] = vhi[v];
+    p_hi_prev = p_hi;
+    MW_Z_ADVANCE(0);                                       // centred on level 1, nxt = level 4
+    __syncthreads();
+  }
+
+  // ---- march over levels -----------------------------------------------------------------------------------
+  for (int k = 0; k < nz; ++k) {
+    const double *Wk = W + (k & 1) * C::SLOTP;
+    int *cA = ctr + (k & 1) * 2, *cB = cA + 1;
+    const double hyc_k = __ldg(P.hyc + k), hytc_k = __ldg(P.hytc + k);
+
+    if (use_tma) {
+      const uint32_t parity = (uint32_t) ((k >> 1) & 1);
+      uint32_t done = 0;
+      for (int spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(&bar[k & 1])), "r"(parity)
+            : "memory");
+        if (spin > (1 << 22)) __trap();                   // a lost TMA must fail loudly, not hang the GPU
+      }
+    }
+
+    // ================= phase A =================
+    double Lz[NH], Rz[NH], pLz, pRz;
+    if (k + 1 < nz) {
+      MW_Z_RECON(k + 1);
+#pragma unroll
+      for (int v = 0; v < NH; ++v) { Lz[v] = vhi_prev[v]; Rz[v] = vlo[v]; }
+      pLz = p_hi_prev; pRz = p_lo;
+    } else {                                               // top boundary face
+#pragma unroll
+      for (int v = 0; v < NH; ++v) {
+        const int l = v0 + v;
+        Lz[v] = vhi_prev[v];
+        if (l == idW && wall) Lz[v] = 0.0;
+        Rz[v] = Lz[v];
+      }
+      pLz = p_hi_prev; pRz = p_hi_prev;
+    }
+    MW_Z_PUBLISH(Lz, Rz, pLz, pRz, k + 1);
+    // values of my cell at level k that phase C needs after the plane slot has been recycled
+    const int pc = (oy + HALO) * PX + (ox + HALO);
+    const double rho_k = Wk[idR * PLANE + pc] + hyc_k;
+    const double u_k = Wk[idU * PLANE + pc], v_k = Wk[idV * PLANE + pc];
+
+    {
+      const int JX = C::XC, JY = P.sim2d ? 0 : C::YC;
+      const int per = JX + JY, total = N * per;
+      run_jobs(cA, total, [&](int idx) {
+        int l, r;
+        if (idx < per) { l = idT; r = idx; }               // heavy jobs (two pows each) first
+        else { r = idx - per; l = r / per; r -= l * per; if (l >= idT) l += 1; }
+        double lo, hi;
+        if (r < JX) {
+          const int c = r, y = c / (TX + 2), xr = c % (TX + 2);     // cell x = xr-1; stencil px = xr .. xr+4
+          const double *row = Wk + l * PLANE + (y + HALO) * PX + xr;
+          weno5_edges(row[0], row[1], row[2], row[3], row[4], lo, hi);
+          Ex[(l * 2 + 0) * C::XC + c] = lo;
+          Ex[(l * 2 + 1) * C::XC + c] = hi;
+          if (l == idT) {
+            Ex[(N * 2 + 0) * C::XC + c] = eos_pressure(lo + hytc_k, P.C0, P.gamma);
+            Ex[(N * 2 + 1) * C::XC + c] = eos_pressure(hi + hytc_k, P.C0, P.gamma);
+          }
+        } else {
+          const int c = r - JX, yr = c / TX, x = c % TX;            // cell y = yr-1; stencil py = yr .. yr+4
+          const double *col = Wk + l * PLANE + yr * PX + (x + HALO);
+          weno5_edges(col[0], col[PX], col[2 * PX], col[3 * PX], col[4 * PX], lo, hi);
+          Ey[(l * 2 + 0) * C::YC + c] = lo;
+          Ey[(l * 2 + 1) * C::YC + c] = hi;
+          if (l == idT) {
+            Ey[(N * 2 + 0) * C::YC + c] = eos_pressure(lo + hytc_k, P.C0, P.gamma);
+            Ey[(N * 2 + 1) * C::YC + c] = eos_pressure(hi + hytc_k, P.C0, P.gamma);
+          }
+        }
+      });
+    }
+    __syncthreads();
+    // plane k is dead: fetch level k+2 into its slot; reset the other parity's job counters
+    if (k + 2 < nz) MW_LOAD_PLANE(k + 2);
+    if (tid == 0) { ctr[((k + 1) & 1) * 2] = 0; ctr[((k + 1) & 1) * 2 + 1] = 0; }
+
+    // ================= phase B =================
+    // q0 of my cell (plain loads: qout may alias q0 in stage 3, all reads happen before the barrier below)
+    double q0v[NH], rho0 = 0.0;
+    if (P.rk_a != 0.0) {
+      const long long cell = (long long) k * P.zstride + colbase;
+      rho0 = P.q0[cell] + hyc_k;
+#pragma unroll
+      for (int v = 0; v < NH; ++v) { const int l = v0 + v; q0v[v] = (l < N) ? P.q0[(long long) l * P.vstride + cell] : 0.0; }
+    } else {
+#pragma unroll
+      for (int v = 0; v < NH; ++v) q0v[v] = 0.0;
+    }
+    {
+      const int JX = C::XF, JY = P.sim2d ? 0 : C::YF;
+      run_jobs(cB, JX + JY, [&](int idx) {
+        const bool isx = idx < JX;
+        const double *E; int cL, cR, stride, x, y, fs, fc;
+        double *F;
+        if (isx) { y = idx / (TX + 1); x = idx % (TX + 1); E = Ex; stride = C::XC; cL = y * (TX + 2) + x; cR = cL + 1;
+                   F = Fx; fs = C::XF; fc = idx; }
+        else { fc = idx - JX; y = fc / TX; x = fc % TX; E = Ey; stride = C::YC; cL = y * TX + x; cR = cL + TX;
+               F = Fy; fs = C::YF; }
+        const int idN = isx ? idU : idV;                    // the normal velocity
+        const double rL = E[(idR * 2 + 1) * stride + cL] + hyc_k, rR = E[(idR * 2 + 0) * stride + cR] + hyc_k;
+        const double mL = E[(idN * 2 + 1) * stride + cL] * rL, mR = E[(idN * 2 + 0) * stride + cR] * rR;
+        double m_upw, p_upw; bool upL;
+        riemann(E[(N * 2 + 1) * stride + cL], E[(N * 2 + 0) * stride + cR], mL, mR, m_upw, p_upw, upL);
+        const int cu = upL ? cL : cR, su = upL ? 1 : 0;
+        const double r_up = upL ? rL : rR;
+        const int gfi = i0 + x, gfj = j0 + y;
+        const bool wr = isx ? (gfi <= P.nx && gfj < P.ny) : (gfi < P.nx && gfj <= P.ny);
+#pragma unroll
+        for (int l = 0; l < N; ++l) {
+          double f;
+          if (l == idR) f = m_upw;
+          else {
+            const double q_up = E[(l * 2 + su) * stride + cu];
+            if (l == idT) f = m_upw * (q_up + hytc_k) * fast_rcp(r_up);
+            else f = m_upw * q_up;
+            if (l == idN) f += p_upw;
+          }
+          F[l * fs + fc] = f;
+          if (l >= NUM_STATE && wr) {
+            if (isx) P.flux_x[(((long long) (l - NUM_STATE) * nz + k) * P.ny + gfj) * (P.nx + 1) + gfi] = f;
+            else     P.flux_y[(((long long) (l - NUM_STATE) * nz + k) * (P.ny + 1) + gfj) * P.nx + gfi] = f;
+          }
+        }
+      });
+    }
+    double fz_hi[NH], zm_hi;
+    MW_Z_FLUX(Lz, Rz, k + 1, fz_hi, zm_hi);
+    __syncthreads();
+
+    // ================= phase C =================
+    {
+      const int fxi = oy * (TX + 1) + ox, fyi = oy * TX + ox;
+      const double dtI = P.dt_stage, tau = 1.e3 * P.dt_stage;
+      const double imm_c = -fmin(1.0, dtI / tau) / dtI;      // immersed tendency = imm_c * q   (DYC:536-542)
+      double prop = 0.0;
+      if (P.use_immersed && in_dom) prop = __ldg(P.immersed + ((long long) k * P.ny + gj) * P.nx + gi);
+      // new density (needed by every owner to store divided variables)
+      double tR = -(Fx[idR * C::XF + fxi + 1] - Fx[idR * C::XF + fxi]) * P.rdx;
+      if (!P.sim2d) tR -= (Fy[idR * C::YF + fyi + TX] - Fy[idR * C::YF + fyi]) * P.rdy;
+      tR -= (zm_hi - zm_lo) * P.rdz;
+      const double rhoP_k = rho_k - hyc_k;
+      if (P.use_immersed) tR = prop * (imm_c * rhoP_k) + (1.0 - prop) * tR;
+      const double rhoP_new = (P.rk_a * (rho0 - hyc_k) + P.rk_b * rhoP_k) + P.rk_cdt * tR;
+      const double r_new = fast_rcp(rhoP_new + hyc_k);
+#pragma unroll
+      for (int v = 0; v < NH; ++v) {
+        const int l = v0 + v;
+        if (l < N && in_dom) {
+          const double val_k = win[v][1];                    // level k (the window is centred on k+1)
+          double t = -(Fx[l * C::XF + fxi + 1] - Fx[l * C::XF + fxi]) * P.rdx;
+          if (!P.sim2d) t -= (Fy[l * C::YF + fyi + TX] - Fy[l * C::YF + fyi]) * P.rdy;
+          t -= (fz_hi[v] - fz_lo[v]) * P.rdz;
+          double qc, q0c;                                    // conserved values of the stage input and of q0
+          if (l == idR || l == idT) { qc = val_k; q0c = q0v[v]; }
+          else { qc = val_k * rho_k; q0c = q0v[v] * rho0; }
+          if (l == idW && P.enable_gravity) t += -P.grav * rho_k;
+          if (l == idU) t += P.fcor * (v_k * rho_k);
+          if (l == idV) t -= P.fcor * (u_k * rho_k);
+          if (l == idV && P.sim2d) t = 0.0;
+          if (l < NUM_STATE) {
+            if (P.use_immersed) t = prop * (imm_c * qc) + (1.0 - prop) * t;
+            if (l == idR) {
+              store_with_images(P.qout, P, k, gj, gi, rhoP_new);
+            } else {
+              const double qn = (P.rk_a * q0c + P.rk_b * qc) + P.rk_cdt * t;
+              store_with_images(P.qout + (long long) l * P.vstride, P, k, gj, gi, (l == idT) ? qn : qn * r_new);
+            }
+          } else {
+            // tracer: leave the RK base value in qout and the FCT factor in mult for k_tracer_update
+            const int tr = l - NUM_STATE;
+            double m = 1.0;
+            if ((P.positive_mask >> tr) & 1u) {                // DYC:498-516
+              const double vol = P.dx * P.dy * P.dz;
+              const double mass_available = fmax(qc, 0.0) * vol;
+              const double fox = (fmax(Fx[l * C::XF + fxi + 1], 0.0) - fmin(Fx[l * C::XF + fxi], 0.0)) * P.rdx;
+              const double foy = P.sim2d ? 0.0
+                                 : (fmax(Fy[l * C::YF + fyi + TX], 0.0) - fmin(Fy[l * C::YF + fyi], 0.0)) * P.rdy;
+              const double foz = (fmax(fz_hi[v], 0.0) - fmin(fz_lo[v], 0.0)) * P.rdz;
+              const double mass_out = (fox + foy + foz) * P.dt_stage * vol;
+              if (mass_out > mass_available) m = mass_available / mass_out;
+            }
+            const long long cidx = (((long long) tr * nz + k) * P.ny + gj) * P.nx + gi;
+            P.mult[cidx] = m;
+            P.qout[(long long) l * P.vstride + (long long) k * P.zstride + (long long) (gj + HALO) * P.pitch + gi + HALO] =
+                P.rk_a * q0c + P.rk_b * qc;
+          }
+        }
+      }
+    }
+    // roll the z state
+#pragma unroll
+    for (int v = 0; v < NH; ++v) { fz_lo[v] = fz_hi[v]; vhi_prev[v] = vhi[v]; }
+    zm_lo = zm_hi;
+    p_hi_prev = p_hi;
+    MW_Z_ADVANCE(k + 1);
+    // no barrier needed here: phase A(k+1) touches Ex/Ey/Zs only, which phase C does not read
+  }
+#undef MW_LOAD_PLANE
+#undef MW_ZLOAD
+#undef MW_Z_RECON
+#undef MW_Z_PUBLISH
+#undef MW_Z_FLUX
+#undef MW_Z_ADVANCE
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Tracer finish: apply the donor cell's FCT factor to every face flux (DYC:506-514), take the divergence
+// (DYC:529-533), complete the RK combination, clip positive tracers (DYC:127-130) and store concentrations.
+// Across the global periodic seam the donor's factor is NOT applied, which is what the reference does with its
+// two independent copies of that face.
+// --------------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256) k_tracer_update(const StageParams P) {
+  const long long ncell = (long long) P.nz * P.ny * P.nx;
+  const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const int i = (int) (c % P.nx), j = (int) ((c / P.nx) % P.ny), k = (int) (c / ((long long) P.nx * P.ny));
+  const long long hcell = (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + i + HALO;
+  const double r_new = fast_rcp(P.qout[hcell] + __ldg(P.hyc + k));
+  const long long pl = (long long) P.ny * P.nx;
+#pragma unroll
+  for (int tr = 0; tr < NT; ++tr) {
+    const double *FXp = P.flux_x + (((long long) tr * P.nz + k) * P.ny + j) * (P.nx + 1) + i;
+    const double *FZp = P.flux_z + ((long long) tr * (P.nz + 1) + k) * pl + (long long) j * P.nx + i;
+    const double *Mp = P.mult + (long long) tr * ncell + c;
+    double fxl = FXp[0], fxh = FXp[1], fzl = FZp[0], fzh = FZp[pl], fyl = 0.0, fyh = 0.0;
+    if (!P.sim2d) {
+      const double *FYp = P.flux_y + (((long long) tr * P.nz + k) * (P.ny + 1) + j) * P.nx + i;
+      fyl = FYp[0]; fyh = FYp[P.nx];
+    }
+    if ((P.positive_mask >> tr) & 1u) {
+      const double ms = Mp[0];
+      // TODO(multi-GPU): donors across a rank boundary use factor 1, like the reference's rank boundaries
+      if (fxl > 0) { if (i > 0) fxl *= Mp[-1]; }                 else if (fxl < 0) fxl *= ms;
+      if (fxh < 0) { if (i < P.nx - 1) fxh *= Mp[1]; }           else if (fxh > 0) fxh *= ms;
+      if (fyl > 0) { if (j > 0) fyl *= Mp[-P.nx]; }              else if (fyl < 0) fyl *= ms;
+      if (fyh < 0) { if (j < P.ny - 1) fyh *= Mp[P.nx]; }        else if (fyh > 0) fyh *= ms;
+      if (fzl > 0) { if (k > 0) fzl *= Mp[-pl]; }                else if (fzl < 0) fzl *= ms;
+      if (fzh < 0) { if (k < P.nz - 1) fzh *= Mp[pl]; }          else if (fzh > 0) fzh *= ms;
+    }
+    const double t = -(fxh - fxl) * P.rdx - (fyh - fyl) * P.rdy - (fzh - fzl) * P.rdz;
+    double *qv = P.qout + (long long) (NUM_STATE + tr) * P.vstride;
+    double qn = qv[hcell] + P.rk_cdt * t;
+    if ((P.positive_mask >> tr) & 1u) qn = fmax(0.0, qn);
+    store_with_images(qv, P, k, j, i, qn * r_new);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Coupler <-> dycore form (DYC:1955-2015 and DYC:1891-1951)
+// --------------------------------------------------------------------------------------------------------
+struct ConvertParams {
+  StageParams S;                                   // geometry, profiles, constants (qout = dycore-form buffer)
+  double *fields[NUM_STATE + MW_MAX_TRACERS];      // coupler fields [nz][ny][nx]
+  double R_d, R_v;
+  int idWV;
+  unsigned adds_mass_mask;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256) k_coupler_to_dyn(const ConvertParams Q) {
+  const StageParams &P = Q.S;
+  const long long ncell = (long long) P.nz * P.ny * P.nx;
+  const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const int i = (int) (c % P.nx), j = (int) ((c / P.nx) % P.ny), k = (int) (c / ((long long) P.nx * P.ny));
+  const double rho_d = Q.fields[0][c], u = Q.fields[1][c], v = Q.fields[2][c], w = Q.fields[3][c], temp = Q.fields[4][c];
+  double trv[NT > 0 ? NT : 1];
+  double rho = rho_d;
+#pragma unroll
+  for (int tr = 0; tr < NT; ++tr) {
+    trv[tr] = Q.fields[NUM_STATE + tr][c];
+    if ((Q.adds_mass_mask >> tr) & 1u) rho += trv[tr];
+  }
+  double rho_v = 0.0;
+#pragma unroll
+  for (int tr = 0; tr < NT; ++tr) if (tr == Q.idWV) rho_v = trv[tr];
+  const double press = rho_d * Q.R_d * temp + rho_v * Q.R_v * temp;
+  const double rt = pow(press / P.C0, 1.0 / P.gamma);          // rho*theta
+  store_with_images(P.qout + (long long) idR * P.vstride, P, k, j, i, rho - __ldg(P.hyc + k));
+  store_with_images(P.qout + (long long) idU * P.vstride, P, k, j, i, u);
+  store_with_images(P.qout + (long long) idV * P.vstride, P, k, j, i, v);
+  store_with_images(P.qout + (long long) idW * P.vstride, P, k, j, i, w);
+  store_with_images(P.qout + (long long) idT * P.vstride, P, k, j, i, rt - __ldg(P.hytc + k));
+  const double r = 1.0 / rho;
+#pragma unroll
+  for (int tr = 0; tr < NT; ++tr)
+    store_with_images(P.qout + (long long) (NUM_STATE + tr) * P.vstride, P, k, j, i, trv[tr] * r);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256) k_dyn_to_coupler(const ConvertParams Q) {
+  const StageParams &P = Q.S;
+  const long long ncell = (long long) P.nz * P.ny * P.nx;
+  const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const int i = (int) (c % P.nx), j = (int) ((c / P.nx) % P.ny), k = (int) (c / ((long long) P.nx * P.ny));
+  const long long h = (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + i + HALO;
+  const double *q = P.qin;
+  const double rho = q[h] + __ldg(P.hyc + k);
+  const double rt = q[(long long) idT * P.vstride + h] + __ldg(P.hytc + k);
+  const double press = P.C0 * pow(rt, P.gamma);
+  double rho_d = rho, rho_v = 0.0;
+#pragma unroll
+  for (int tr = 0; tr < NT; ++tr) {
+    const double m = q[(long long) (NUM_STATE + tr) * P.vstride + h] * rho;
+    Q.fields[NUM_STATE + tr][c] = m;
+    if ((Q.adds_mass_mask >> tr) & 1u) rho_d -= m;
+    if (tr == Q.idWV) rho_v = m;
+  }
+  Q.fields[0][c] = rho_d;
+  Q.fields[1][c] = q[(long long) idU * P.vstride + h];
+  Q.fields[2][c] = q[(long long) idV * P.vstride + h];
+  Q.fields[3][c] = q[(long long) idW * P.vstride + h];
+  Q.fields[4][c] = press / (rho_d * Q.R_d + rho_v * Q.R_v);
+}
+
+// kernel-level test hook for the WENO building block
+__global__ void k_weno5_edges(const double *__restrict__ s, double *__restrict__ out, long long n) {
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double lo, hi;
+  weno5_edges(s[5 * i], s[5 * i + 1], s[5 * i + 2], s[5 * i + 3], s[5 * i + 4], lo, hi);
+  out[2 * i] = lo;
+  out[2 * i + 1] = hi;
+}
+
+}  // namespace mw

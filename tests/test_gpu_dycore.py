@@ -1,0 +1,188 @@
+"""GPU parity tests of the dycore (WENO5 + upwind fluxes + FCT + SSPRK3), through the C ABI of libmwb200.so,
+against (a) the golden fixtures produced by the compiled reference and (b) the plain-C oracle on the same inputs.
+Tolerance from BASELINE.json north_star: fp64 max relative state difference <= 1e-9 after a fixed short run."""
+import os
+import numpy as np
+import pytest
+
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def relmax(a, b):
+    den = np.abs(b).max()
+    return np.abs(a - b).max() / (den if den > 0 else 1.0)
+
+
+def gpu_run(g, s0, steps, dt, T, immersed=None, **cfgkw):
+    import torch
+    import miniweatherml_b200 as mw
+    nz, ny, nx = s0.shape[1:]
+    cfg = mw.make_config(nx, ny, nz, float(g["xlen"]), float(g["ylen"]), float(g["zlen"]), T,
+                         use_immersed=immersed is not None, **cfgkw)
+    dy = mw.Dycore(cfg)
+    dy.set_background(g["bg"])
+    if immersed is not None:
+        imm = torch.tensor(immersed, device="cuda", dtype=torch.float64)
+        dy.set_immersed(imm)
+    fields = [torch.tensor(np.ascontiguousarray(s0[l]), device="cuda", dtype=torch.float64) for l in range(5 + T)]
+    for _ in range(steps):
+        dy.time_step(fields, dt)
+    torch.cuda.synchronize()
+    out = np.stack([f.cpu().numpy() for f in fields])
+    launches = dy.launch_count()
+    dy.close()
+    return out, launches
+
+
+def test_weno5_kernel_vs_reference_kat(golden):
+    import torch
+    import miniweatherml_b200 as mw
+    g = golden("weno5_kat.npz")
+    st = torch.tensor(g["stencils"], device="cuda")
+    out = mw.weno5_edges(st).cpu().numpy()
+    scale = np.abs(g["stencils"]).max(axis=1, keepdims=True)
+    scale[scale == 0] = 1.0
+    assert (np.abs(out - g["gll"]) / scale).max() <= 1e-12
+
+
+def test_weno5_kernel_vs_oracle_random():
+    import torch
+    import miniweatherml_b200 as mw
+    rng = np.random.default_rng(7)
+    st = np.concatenate([rng.standard_normal((4096, 5)) * 10.0 ** rng.integers(-8, 4, (4096, 1)),
+                         1.0 + 1e-6 * rng.standard_normal((1024, 5))])
+    ref = O.weno5(st)
+    out = mw.weno5_edges(torch.tensor(st, device="cuda")).cpu().numpy()
+    scale = np.abs(st).max(axis=1, keepdims=True)
+    assert (np.abs(out - ref) / scale).max() <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["config1_dycore10.npz", "box3d_vapor_dycore5.npz"])
+def test_dycore_vs_reference_golden(golden, name):
+    g = golden(name)
+    T = g["s0"].shape[0] - 5
+    out, launches = gpu_run(g, g["s0"], int(g["steps"]), float(g["dt"]), T)
+    assert launches > 0
+    for l in range(5 + T):
+        assert relmax(out[l], g["s1"][l]) <= TOL, (l, relmax(out[l], g["s1"][l]))
+
+
+def test_dycore_three_tracers_vs_oracle(golden):
+    """Kessler's three tracers advected by the dycore alone, from a state with cloud and rain (FCT active)."""
+    g = golden("config1_restart1000_full10.npz")
+    s0 = g["s0"]
+    p = O.make_params(int(g["nx"]), 1, int(g["nz"]), float(g["xlen"]), float(g["ylen"]), float(g["zlen"]), 3)
+    ref = s0.copy()
+    O.dycore_step(p, g["bg"], ref, float(g["dt"]), steps=6)
+    out, _ = gpu_run(g, s0, 6, float(g["dt"]), 3)
+    for l in range(8):
+        assert relmax(out[l], ref[l]) <= TOL, (l, relmax(out[l], ref[l]))
+
+
+def synthetic_state(g, nz, ny, nx, T, seed):
+    """Smooth random perturbation of a golden initial column, tiled to (nz, ny, nx); ragged sizes on purpose."""
+    rng = np.random.default_rng(seed)
+    base = g["s0"]                                   # [5+Tg][nzg][nyg][nxg]
+    assert base.shape[1] == nz
+    col = base[:, :, 0, 0]
+    s = np.empty((5 + T, nz, ny, nx))
+    x = np.arange(nx)[None, None, :] / nx
+    y = np.arange(ny)[None, :, None] / ny
+    z = np.arange(nz)[:, None, None] / nz
+    bump = np.sin(2 * np.pi * (x + 0.3 * y)) * np.cos(2 * np.pi * (y - 0.2 * z)) * np.sin(np.pi * z)
+    s[0] = col[0][:, None, None] * (1 + 2e-3 * bump)
+    s[1] = col[1][:, None, None] + 3.0 * bump
+    s[2] = 2.0 * np.roll(bump, 3, axis=2) if ny > 1 else 0.0
+    s[3] = 1.0 * np.roll(bump, 5, axis=1 if ny > 1 else 2) * np.sin(np.pi * z)
+    s[4] = col[4][:, None, None] + 1.5 * bump
+    s[5] = col[5][:, None, None] * (1 + 0.3 * bump)
+    for t in range(1, T):
+        blob = np.exp(-(((x - 0.05 - 0.4 * t) ** 2) / 0.005 + ((y - 0.9) ** 2) / 0.02 + ((z - 0.3) ** 2) / 0.02))
+        s[5 + t] = 2e-3 * blob * (blob > 0.05)       # compact blobs touching the periodic seam: FCT + clipping active
+    s += 0 * rng.random(s.shape)
+    return np.ascontiguousarray(s)
+
+
+@pytest.mark.parametrize("nx,ny,T", [(37, 19, 1), (45, 11, 3), (70, 1, 3), (33, 9, 0), (64, 16, 2)])
+def test_dycore_ragged_sizes_vs_oracle(golden, nx, ny, T):
+    g = golden("box3d_vapor_dycore5.npz")
+    nz = int(g["nz"])
+    gg = dict(xlen=nx * 1000.0, ylen=max(ny, 1) * 1000.0, zlen=float(g["zlen"]), bg=g["bg"])
+    s0 = synthetic_state(g, nz, ny, nx, max(T, 1), seed=nx * 100 + ny)
+    dt = 0.6 * min(1000.0, float(g["zlen"]) / nz) / 430.0
+    if T == 0:
+        s0[5] = 0.0                                   # dry: the oracle still carries a (zero) vapour field
+        p = O.make_params(nx, ny, nz, gg["xlen"], gg["ylen"], gg["zlen"], 1)
+        ref = s0.copy()
+        O.dycore_step(p, g["bg"], ref, dt, steps=3)
+        out, _ = gpu_run(gg, s0[:5], 3, dt, 0)
+        ref = ref[:5]
+    else:
+        p = O.make_params(nx, ny, nz, gg["xlen"], gg["ylen"], gg["zlen"], T)
+        ref = s0.copy()
+        O.dycore_step(p, g["bg"], ref, dt, steps=3)
+        out, _ = gpu_run(gg, s0, 3, dt, T)
+    for l in range(ref.shape[0]):
+        assert relmax(out[l], ref[l]) <= TOL, (l, relmax(out[l], ref[l]))
+
+
+def test_dycore_immersed_and_subcycling_vs_oracle(golden):
+    g = golden("box3d_vapor_dycore5.npz")
+    nz, ny, nx = g["s0"].shape[1:]
+    imm = np.zeros((nz, ny, nx))
+    imm[:4, 5:9, 6:10] = 1.0
+    imm[4, 5:9, 6:10] = 0.5
+    p = O.make_params(nx, ny, nz, float(g["xlen"]), float(g["ylen"]), float(g["zlen"]), 1, use_immersed=True)
+    ref = g["s0"].copy()
+    dt = 2.5 * float(g["dt"])                          # forces ncycles = 3 (DYC:104-108)
+    O.dycore_step(p, g["bg"], ref, dt, immersed=imm, steps=2)
+    out, _ = gpu_run(g, g["s0"], 2, dt, 1, immersed=imm)
+    for l in range(6):
+        assert relmax(out[l], ref[l]) <= TOL, (l, relmax(out[l], ref[l]))
+
+
+def test_mass_conservation_to_roundoff(golden):
+    g = golden("box3d_vapor_dycore5.npz")
+    p = O.make_params(int(g["nx"]), int(g["ny"]), int(g["nz"]), float(g["xlen"]), float(g["ylen"]), float(g["zlen"]), 1)
+    m0 = O.masses(p, np.ascontiguousarray(g["s0"]))
+    out, _ = gpu_run(g, g["s0"], 10, float(g["dt"]), 1)
+    m1 = O.masses(p, np.ascontiguousarray(out))
+    assert np.all(np.abs(m1 - m0) <= 5e-14 * np.abs(m0)), (m1 - m0) / m0
+
+
+def test_tma_and_plain_load_paths_agree(golden, monkeypatch):
+    g = golden("box3d_vapor_dycore5.npz")
+    a, _ = gpu_run(g, g["s0"], 2, float(g["dt"]), 1)
+    monkeypatch.setenv("MW_NO_TMA", "1")
+    b, _ = gpu_run(g, g["s0"], 2, float(g["dt"]), 1)
+    assert np.array_equal(a, b)
+
+
+def test_host_buffer_entry_point(golden):
+    import miniweatherml_b200 as mw
+    g = golden("box3d_vapor_dycore5.npz")
+    nz, ny, nx = g["s0"].shape[1:]
+    cfg = mw.make_config(nx, ny, nz, float(g["xlen"]), float(g["ylen"]), float(g["zlen"]), 1)
+    dy = mw.Dycore(cfg)
+    dy.set_background(g["bg"])
+    host = [np.ascontiguousarray(g["s0"][l]).copy() for l in range(6)]
+    for _ in range(int(g["steps"])):
+        dy.time_step_host(host, float(g["dt"]))
+    for l in range(6):
+        assert relmax(host[l], g["s1"][l]) <= TOL
+    dy.close()
+
+
+def test_unsupported_configs_fail_loudly():
+    import miniweatherml_b200 as mw
+    cfg = mw.make_config(32, 32, 16, 32e3, 32e3, 16e3, 1)
+    cfg.nens = 2
+    with pytest.raises(mw.MwError):
+        mw.Dycore(cfg)
+    cfg = mw.make_config(32, 32, 16, 32e3, 32e3, 16e3, 1)
+    cfg.bc_x = 2
+    with pytest.raises(mw.MwError):
+        mw.Dycore(cfg)
