@@ -108,7 +108,10 @@ static StageParams base_params(const mw_dycore *h) {
   P.nx = c.nx; P.ny = c.ny; P.nz = c.nz;
   P.pitch = h->pitch; P.zstride = h->zstride; P.vstride = h->vstride;
   P.flux_x = h->flux_x; P.flux_y = h->flux_y; P.flux_z = h->flux_z; P.mult = h->mult;
-  P.hyc = h->bg; P.hytc = h->bg + c.nz; P.hye = h->bg + 2 * c.nz; P.hyte = h->bg + 2 * c.nz + (c.nz + 1);
+  P.hyc = h->bg; P.hytc = h->bg + c.nz; P.hye = h->bg + 2 * c.nz; P.hyte = h->bg + 3 * c.nz + 1;
+  P.ihytc = h->bg + 4 * c.nz + 2; P.pcell = P.ihytc + c.nz; P.ihyte = P.pcell + c.nz; P.pedge = P.ihyte + c.nz + 1;
+  P.pser[0] = 1.0;                                         // C(gamma, n)
+  for (int n = 1; n < 12; ++n) P.pser[n] = P.pser[n - 1] * (c.gamma_d - (n - 1)) / n;
   P.immersed = h->immersed;
   P.dx = h->dx; P.dy = h->dy; P.dz = h->dz;
   P.rdx = 1.0 / h->dx; P.rdy = 1.0 / h->dy; P.rdz = 1.0 / h->dz;
@@ -179,7 +182,7 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   if (ce == cudaSuccess) ce = cudaMalloc(&h->flux_y, T * nzl * (nyl + 1) * nxl * 8);
   if (ce == cudaSuccess) ce = cudaMalloc(&h->flux_z, T * (nzl + 1) * nyl * nxl * 8);
   if (ce == cudaSuccess) ce = cudaMalloc(&h->mult, T * nzl * nyl * nxl * 8);
-  if (ce == cudaSuccess) ce = cudaMalloc(&h->bg, (4 * nzl + 2) * 8);
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->bg, (8 * nzl + 4) * 8);
   if (ce != cudaSuccess) {
     set_error("mw_dycore_create: device allocation failed: %s", cudaGetErrorString(ce));
     mw_dycore_destroy(h);
@@ -215,7 +218,13 @@ extern "C" int mw_dycore_set_background(mw_dycore *h, const double *hyc, const d
   memcpy(&h->bg_host[nz], hytc, nz * 8);
   memcpy(&h->bg_host[2 * nz], hye, (nz + 1) * 8);
   memcpy(&h->bg_host[3 * nz + 1], hyte, (nz + 1) * 8);
-  MW_CUDA_OK(cudaMemcpy(h->bg, h->bg_host.data(), h->bg_host.size() * 8, cudaMemcpyHostToDevice));
+  // derived tables for the in-kernel equation of state: 1/bg and C0*bg^gamma at cell centres and z edges
+  std::vector<double> all(8 * nz + 4);
+  memcpy(all.data(), h->bg_host.data(), (4 * nz + 2) * 8);
+  double *ihytc = &all[4 * nz + 2], *pcell = ihytc + nz, *ihyte = pcell + nz, *pedge = ihyte + nz + 1;
+  for (int k = 0; k < nz; ++k) { ihytc[k] = 1.0 / hytc[k]; pcell[k] = h->cfg.C0 * pow(hytc[k], h->cfg.gamma_d); }
+  for (int k = 0; k <= nz; ++k) { ihyte[k] = 1.0 / hyte[k]; pedge[k] = h->cfg.C0 * pow(hyte[k], h->cfg.gamma_d); }
+  MW_CUDA_OK(cudaMemcpy(h->bg, all.data(), all.size() * 8, cudaMemcpyHostToDevice));
   h->bg_set = true;
   return MW_OK;
 }

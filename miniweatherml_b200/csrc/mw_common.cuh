@@ -47,58 +47,52 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // WENO5 reconstruction of the two edge values of the centre cell from five cell averages s0..s4.
 // Same mathematics as the reference's WenoLimiter<5>::compute_limited_coefs + coefs_to_gll
 // (model/modules/helpers/WenoLimiter.h:68-93, WenoLimiter_recon.h:12-15,37-56,84-103,155-162,
-//  model/modules/dynamics_euler_stratified_wenofv.h:556-571), restructured for the FP64 pipe:
-//   * candidate polynomials are expressed through first/second/third/fourth differences of the stencil,
+//  model/modules/dynamics_euler_stratified_wenofv.h:556-571), restructured for the FP64 pipe (73 FP64 ops, one
+// MUFU, no division instead of 158 ops with 16 divisions):
+//   * candidate polynomials are expressed through first/second/third/fourth differences of the stencil
+//     (b1 = 2*a1, D = 2*a2, T3 = 12*a3H, E4 = 24*a4H, c2 = 16*a2H); smoothness indicators carry a common factor 4,
 //   * the three convexify() normalisations and the four weight divisions collapse into ONE reciprocal:
 //       w_i ~ idl_i / ((TV_i/S)^2 + 1e-20)  ==  idl_i * S^2 / (TV_i^2 + 1e-20 S^2)  ->  idl_i * prod_{j!=i} d_j / sum(...)
-//     with d_i = TV_i^2 + 1e-20*S^2 (S = sum TV; S := 1 when S <= 1e-20, which is the reference's "do not
-//     normalise" branch),
-//   * edge values are evaluated from the even/odd parts of the blended polynomial (sum w_i = 1).
+//     with d_i = TV_i^2 + 1e-20*S^2 (S = sum TV; S := 1 when S <= 1e-20, the reference's "do not normalise" branch),
+//   * edge values come from the even/odd parts of the blended polynomial (sum w_i = 1), un-normalised weights
+//     first, one multiplication by the reciprocal at the end.
 // Differences to the reference are rounding-level only (<= a few ulp of the stencil magnitude).
+struct WenoConsts { double c133, c524, k2, k2e, k3, k4, i12, i24, tenth, e20; };
+__constant__ WenoConsts wc = {13.0 / 3.0, 5.0 / 24.0, 13.0 / 192.0, 7.0 / 160.0, 3129.0 / 2880.0, 87617.0 / 20160.0,
+                              1.0 / 12.0, 1.0 / 24.0, 0.1, 1.e-20};
 __device__ __forceinline__ void weno5_edges(double s0, double s1, double s2, double s3, double s4,
                                             double &v_lo, double &v_hi) {
   const double d01 = s1 - s0, d12 = s2 - s1, d23 = s3 - s2, d34 = s4 - s3;
-  const double DL = d12 - d01, DC = d23 - d12, DR = d34 - d23;     // second differences (= 2*a2 of L, C, R)
-  const double a1L = fma(0.5, DL, d12);
-  const double a1C = 0.5 * (d12 + d23);
-  const double a1R = fma(-0.5, DR, d23);
-  constexpr double c1312 = 13.0 / 12.0;
-  const double tL = fma(a1L, a1L, (c1312 * DL) * DL);
-  const double tC = fma(a1C, a1C, (c1312 * DC) * DC);
-  const double tR = fma(a1R, a1R, (c1312 * DR) * DR);
-  const double T3 = DR - DL;                                        // third difference  (= 12*a3 of H)
-  const double E4 = (DL + DR) - 2.0 * DC;                           // fourth difference (= 24*a4 of H)
-  const double a1H = fma(-5.0 / 48.0, T3, a1C);
-  const double a2H = fma(-1.0 / 16.0, E4, 0.5 * DC);
-  const double a3H = T3 * (1.0 / 12.0);
-  const double a4H = E4 * (1.0 / 24.0);
-  double tH = a1H * fma(0.5, a3H, a1H);
-  tH = fma(a2H, fma(13.0 / 3.0, a2H, 4.2 * a4H), tH);
-  tH = fma(3129.0 / 80.0 * a3H, a3H, tH);
-  tH = fma(87617.0 / 140.0 * a4H, a4H, tH);
+  const double DL = d12 - d01, DC = d23 - d12, DR = d34 - d23;               // second differences
+  const double b1L = fma(2.0, d12, DL), b1C = d12 + d23, b1R = fma(2.0, d23, -DR);
+  const double tL = fma(b1L, b1L, (wc.c133 * DL) * DL);                      // 4*TV of the three quadratics
+  const double tC = fma(b1C, b1C, (wc.c133 * DC) * DC);
+  const double tR = fma(b1R, b1R, (wc.c133 * DR) * DR);
+  const double T3 = DR - DL, E4 = fma(-2.0, DC, DL + DR);                    // third / fourth difference
+  const double b1H = fma(-wc.c524, T3, b1C);
+  const double c2 = fma(8.0, DC, -E4);
+  double tH = b1H * fma(wc.i12, T3, b1H);                                    // 4*TV of the quartic
+  tH = fma(c2, fma(wc.k2, c2, wc.k2e * E4), tH);
+  tH = fma(wc.k3 * T3, T3, tH);
+  tH = fma(wc.k4 * E4, E4, tH);
   const double S = (tL + tC) + (tR + tH);
-  const double Se = S > 1.e-20 ? S : 1.0;
-  const double eps = (1.e-20 * Se) * Se;
+  const double Se = S > 4.e-20 ? S : 4.0;
+  const double eps = (wc.e20 * Se) * Se;
   const double dL = fma(tL, tL, eps), dC = fma(tC, tC, eps), dR = fma(tR, tR, eps), dH = fma(tH, tH, eps);
   const double pLC = dL * dC, pRH = dR * dH;
-  const double nL = dC * pRH;                   // ideal weights (1,2,1,1000)/1004: the 1/1004 cancels
-  const double nC = 2.0 * (dL * pRH);
-  const double nR = pLC * dH;
-  const double nH = 1000.0 * (pLC * dR);
+  const double nL = dC * pRH, nC = (dL + dL) * pRH, nR = pLC * dH, nH = (1000.0 * pLC) * dR;   // ideal (1,2,1,1000)
   const double inv = fast_rcp((nL + nC) + (nR + nH));
-  const double wL = nL * inv, wC = nC * inv, wR = nR * inv, wH = nH * inv;
-  // even part: s2 + (wL*DL + (wC+wH)*DC + wR*DR)/12 - wH*E4/120 ; odd part: (sum w_i a1_i)/2 + wH*T3/96
-  double ev = wL * DL;
-  ev = fma(wC + wH, DC, ev);
-  ev = fma(wR, DR, ev);
-  ev = fma(1.0 / 12.0, ev, s2);
-  ev = fma(-1.0 / 120.0 * wH, E4, ev);
-  double od = wL * a1L;
-  od = fma(wC, a1C, od);
-  od = fma(wR, a1R, od);
-  od = fma(wH, a1H, od);
-  od = fma(1.0 / 48.0 * wH, T3, od);    // (wH*T3/96) * 2, halved with the rest below
-  od *= 0.5;
+  const double g = fma(-wc.tenth, E4, DC), h = fma(wc.i24, T3, b1H);
+  double ev = nL * DL;
+  ev = fma(nC, DC, ev);
+  ev = fma(nR, DR, ev);
+  ev = fma(nH, g, ev);
+  double od = nL * b1L;
+  od = fma(nC, b1C, od);
+  od = fma(nR, b1R, od);
+  od = fma(nH, h, od);
+  ev = fma(inv * wc.i12, ev, s2);
+  od = (inv * 0.25) * od;
   v_lo = ev - od;
   v_hi = ev + od;
 }

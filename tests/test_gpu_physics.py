@@ -1,0 +1,175 @@
+"""GPU parity tests of Kessler, the ponni surrogate, sponge layer, column nudging and the thermal perturbation,
+through the C ABI, against the reference's golden outputs and the plain-C oracle.  Tolerances: fp64 fields 1e-9
+relative (north_star); MLP 1e-6 absolute on normalised outputs (ponni's own unit-test tolerance); the fp32 FMA path
+is required to be bit-identical to the reference's ponni build."""
+import numpy as np
+import pytest
+
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def relmax(a, b):
+    den = np.abs(b).max()
+    return np.abs(a - b).max() / (den if den > 0 else 1.0)
+
+
+def dev(a):
+    import torch
+    return torch.tensor(np.ascontiguousarray(a), device="cuda")
+
+
+def test_kessler_micro_step_vs_reference_golden(golden):
+    import torch
+    import miniweatherml_b200 as mw
+    g = golden("config1_restart1000_micro1.npz")
+    s0 = g["s0"]
+    nz = s0.shape[1]
+    f = [dev(s0[l]) for l in range(8)]
+    precl = torch.zeros(s0[0][0].shape, device="cuda", dtype=torch.float64)
+    rs = mw.kessler_step(f[4], f[0], f[5], f[6], f[7], precl, float(g["zlen"]) / nz, float(g["dt"]), want_rainsplit=True)
+    assert rs >= 1
+    for l in range(8):
+        assert relmax(f[l].cpu().numpy(), g["s1"][l]) <= TOL, l
+    assert relmax(precl.cpu().numpy().ravel(), g["precl"]) <= TOL
+
+
+def test_kessler_subcycled_columns_vs_oracle(golden):
+    """rainsplit > 1: hand-built rainy columns (same inputs as the reference KAT, but through time_step's interface)."""
+    import torch
+    import miniweatherml_b200 as mw
+    g = golden("kessler_columns_kat.npz")
+    theta, qv, qc, qr, rho, pk = [np.ascontiguousarray(x) for x in g["inp"]]
+    nz, ncol = theta.shape
+    # build coupler-style fields consistent with (theta, q*, rho, pk): temp = theta*pk would not reproduce pk through
+    # the module's own Exner formula, so compare against the oracle's time_step on the same coupler fields instead
+    temp = theta * pk
+    rho_v, rho_c, rho_r = qv * rho, qc * rho, qr * rho
+    ref = [temp.copy(), rho.copy(), rho_v.copy(), rho_c.copy(), rho_r.copy()]
+    rs_ref, precl_ref = O.kessler_step(nz, ncol, float(g["dz"]), 150.0, *ref)
+    assert rs_ref > 1
+    f = [dev(x) for x in (temp, rho, rho_v, rho_c, rho_r)]
+    precl = torch.zeros(ncol, device="cuda", dtype=torch.float64)
+    rs = mw.kessler_step(f[0], f[1], f[2], f[3], f[4], precl, float(g["dz"]), 150.0, want_rainsplit=True)
+    assert rs == rs_ref
+    for a, b in zip(f, ref):
+        assert relmax(a.cpu().numpy(), b) <= TOL
+    assert relmax(precl.cpu().numpy(), precl_ref) <= TOL
+
+
+def test_kessler_edge_cases():
+    import torch
+    import miniweatherml_b200 as mw
+    nz, ncol = 12, 3
+    z = (np.arange(nz)[:, None] + 0.5) * 500.0 * np.ones((1, ncol))
+    pk = 1.0 - 9.81 * z / (1003.0 * 300.0)
+    rho = 1.0e5 * pk ** (1003.0 / 287.0) / (287.0 * 300.0 * pk)
+    temp = 300.0 * pk
+    zero = np.zeros_like(temp)
+    # completely dry column: nothing may change except round-off in temp
+    ref = [temp.copy(), rho.copy(), zero.copy(), zero.copy(), zero.copy()]
+    O.kessler_step(nz, ncol, 500.0, 10.0, *ref)
+    f = [dev(x) for x in (temp, rho, zero, zero, zero)]
+    precl = torch.ones(ncol, device="cuda", dtype=torch.float64)
+    mw.kessler_step(f[0], f[1], f[2], f[3], f[4], precl, 500.0, 10.0)
+    for a, b in zip(f, ref):
+        assert relmax(a.cpu().numpy(), b) <= TOL
+    assert float(precl.abs().max()) == 0.0
+    with pytest.raises(mw.MwError):
+        mw.kessler_step(f[0], f[1], f[2], f[3], f[4], precl, 500.0, 0.0)      # KES:243
+
+
+@pytest.mark.parametrize("tc", [False, True])
+def test_ponni_mlp_vs_reference_kat(golden, tc):
+    import torch
+    import miniweatherml_b200 as mw
+    g = golden("ponni_mlp_kat.npz")
+    y = mw.mlp_forward(g["w"], torch.tensor(g["x"], device="cuda"), use_tensor_cores=tc).cpu().numpy()
+    assert np.abs(y - g["y"]).max() <= 1e-6
+    if not tc:
+        assert np.array_equal(y, g["y"])            # same fp32 operation order and roundings as ponni
+
+
+@pytest.mark.parametrize("tc", [False, True])
+def test_surrogate_vs_oracle(golden, tc):
+    import miniweatherml_b200 as mw
+    g = golden("config1_restart1000_full10.npz")
+    k = golden("ponni_mlp_kat.npz")
+    s = g["s0"]
+    scl_in = np.array([[201.8189, 302.2934], [0.092945546, 1.1441816], [0.0, 0.019461675], [0.0, 0.004399828],
+                       [0.0, 0.015578972]])
+    scl_out = np.array([[201.81894, 302.29324], [0.0, 0.01946172], [0.0, 0.0044183163], [0.0, 0.0155778695]])
+    fl = [np.ascontiguousarray(s[i].ravel()) for i in (4, 0, 5, 6, 7)]
+    ref = O.surrogate(k["w"], scl_in, scl_out, *fl)
+    out = mw.surrogate_forward(k["w"], scl_in, scl_out, *[dev(x) for x in fl], use_tensor_cores=tc)
+    rng = scl_out[:, 1] - scl_out[:, 0]
+    for f in range(4):
+        err = np.abs(out[f].cpu().numpy() - ref[f]).max() / rng[f]
+        assert err <= (1e-6 if tc else 1e-12), (f, err)      # normalised units
+        if f > 0:
+            assert out[f].min().item() >= 0.0
+
+
+def test_sponge_nudge_perturb_vs_oracle(golden):
+    import miniweatherml_b200 as mw
+    g = golden("box3d_kessler_full4.npz")
+    s0 = g["s0"]
+    nz, ny, nx = s0.shape[1:]
+    dz, zlen, dt = float(g["zlen"]) / nz, float(g["zlen"]), float(g["dt"])
+    ref = s0.copy()
+    O.sponge(ref, dz, zlen, dt)
+    f = [dev(s0[l]) for l in range(8)]
+    mw.sponge_layer(f, dz, zlen, dt)
+    for l in range(8):
+        assert relmax(f[l].cpu().numpy(), ref[l]) <= 1e-13, l
+    # nudging: target column from the initial state, applied to the sponge result
+    idx = [0, 1, 2, 4, 5]
+    col_ref = O.column_average([np.ascontiguousarray(s0[i]) for i in idx])
+    col = mw.column_average([dev(s0[i]) for i in idx])
+    assert relmax(col.cpu().numpy(), col_ref) <= 1e-13
+    r5 = [np.ascontiguousarray(ref[i]) for i in idx]
+    O.nudge(r5, col_ref, dt)
+    mw.nudge_to_column([f[i] for i in idx], col, dt)
+    for a, i in zip(r5, idx):
+        assert relmax(f[i].cpu().numpy(), a) <= 1e-13
+    # thermal bubble
+    t_ref = np.ascontiguousarray(s0[4]).copy()
+    dx, dy = float(g["xlen"]) / nx, float(g["ylen"]) / ny
+    O.perturb_thermal(t_ref, 0, 0, dx, dy, dz, float(g["xlen"]), float(g["ylen"]))
+    t = dev(s0[4])
+    mw.perturb_temperature(t, 0, 0, dx, dy, dz, float(g["xlen"]), float(g["ylen"]))
+    assert relmax(t.cpu().numpy(), t_ref) <= 1e-14
+
+
+def full_step_gpu(mw, dy, f, precl, column, dz, zlen, dt):
+    dy.time_step(f, dt)
+    mw.kessler_step(f[4], f[0], f[5], f[6], f[7], precl, dz, dt)
+    mw.sponge_layer(f, dz, zlen, dt)
+    mw.nudge_to_column([f[0], f[1], f[2], f[4], f[5]], column, dt)
+
+
+@pytest.mark.parametrize("name", ["config1_full10.npz", "config1_restart1000_full10.npz", "box3d_kessler_full4.npz"])
+def test_full_physics_step_vs_reference_golden(golden, name):
+    """The canonical loop of experiments/supercell_example/driver.cpp:73-76 (dycore, Kessler, sponge, nudging)."""
+    import torch
+    import miniweatherml_b200 as mw
+    g = golden(name)
+    s0 = g["s0"]
+    nz, ny, nx = s0.shape[1:]
+    dz, zlen, dt = float(g["zlen"]) / nz, float(g["zlen"]), float(g["dt"])
+    cfg = mw.make_config(nx, ny, nz, float(g["xlen"]), float(g["ylen"]), zlen, 3)
+    dy = mw.Dycore(cfg)
+    dy.set_background(g["bg"])
+    # nudging target: column average of the un-perturbed initial state (driver.cpp:60-61)
+    si = (g["s_init"] if "s_init" in g else s0).copy()
+    si[4] = np.broadcast_to(si[4][:, :1, :1], si[4].shape)
+    column = mw.column_average([dev(si[i]) for i in (0, 1, 2, 4, 5)])
+    f = [dev(s0[l]) for l in range(8)]
+    precl = torch.zeros((ny, nx), device="cuda", dtype=torch.float64)
+    for _ in range(int(g["steps"])):
+        full_step_gpu(mw, dy, f, precl, column, dz, zlen, dt)
+    for l in range(8):
+        assert relmax(f[l].cpu().numpy(), g["s1"][l]) <= TOL, (l, relmax(f[l].cpu().numpy(), g["s1"][l]))
+    dy.close()
