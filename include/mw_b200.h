@@ -77,6 +77,7 @@ int  mw_config_defaults(mw_config *cfg);
 /* ---- dycore ------------------------------------------------------------------------------------------- */
 int  mw_dycore_create(const mw_config *cfg, mw_dycore **out);
 int  mw_dycore_destroy(mw_dycore *h);
+int  mw_dycore_get_config(const mw_dycore *h, mw_config *out);
 /* host pointers: hy_dens_cells[nz], hy_dens_theta_cells[nz], hy_dens_edges[nz+1], hy_dens_theta_edges[nz+1] */
 int  mw_dycore_set_background(mw_dycore *h, const double *hy_dens_cells, const double *hy_dens_theta_cells,
                               const double *hy_dens_edges, const double *hy_dens_theta_edges);

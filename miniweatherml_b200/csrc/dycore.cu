@@ -2,6 +2,7 @@
 // scratch, the background profiles and the TMA descriptors, and sequences the kernels of one time_step
 // (reference: model/modules/dynamics_euler_stratified_wenofv.h:81-198).
 #include "dycore_kernels.cuh"
+#include "comm.cuh"
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -72,8 +73,10 @@ int encode_tensor_map_f64_4d(CUtensorMap *map, const void *base, const uint64_t 
 
 using namespace mw;
 
-// tile of columns one CTA owns; two threads per column
-constexpr int TILE_X = 32, TILE_Y = 8;
+// tile of columns one CTA owns (two threads per column); narrower with >= 3 tracers so the CTA fits 227 KB of smem
+template <int NT> struct Tile { static constexpr int X = (NT <= 2) ? 32 : 24, Y = 8; };
+static int tile_x(int nt) { return nt <= 2 ? 32 : 24; }
+static int tile_y(int) { return 8; }
 
 struct mw_dycore {
   mw_config cfg;
@@ -95,6 +98,11 @@ struct mw_dycore {
   // staging for the *_host entry point
   double *dev_fields[NUM_STATE + MW_MAX_TRACERS] = {nullptr};
   bool dev_fields_alloc = false;
+  // halo exchange over NCCL (decomposed directions only): 0 = W, 1 = E, 2 = S, 3 = N
+  bool dir_active[4] = {false, false, false, false};
+  int peer[4] = {0, 0, 0, 0};
+  double *hsend[4] = {nullptr}, *hrecv[4] = {nullptr}, *msend[4] = {nullptr}, *mrecv[4] = {nullptr};
+  size_t hcount[4] = {0}, mcount[4] = {0};
   // timing
   bool timing = false;
   std::vector<cudaEvent_t> ev;         // [0]=step begin, [1]=step end, then pairs per stage kernel
@@ -127,6 +135,11 @@ static StageParams base_params(const mw_dycore *h) {
   for (int t = 0; t < c.num_tracers; ++t) if (c.tracer_positive[t]) pm |= 1u << t;
   P.positive_mask = pm;
   P.use_tma = h->use_tma;
+  // FCT donors across interior rank boundaries (never across the global periodic seam, see StageParams)
+  P.mult_W = (h->dir_active[0] && c.px > 0) ? h->mrecv[0] : nullptr;
+  P.mult_E = (h->dir_active[1] && c.px < c.nproc_x - 1) ? h->mrecv[1] : nullptr;
+  P.mult_S = (h->dir_active[2] && c.py > 0) ? h->mrecv[2] : nullptr;
+  P.mult_N = (h->dir_active[3] && c.py < c.nproc_y - 1) ? h->mrecv[3] : nullptr;
   return P;
 }
 
@@ -191,7 +204,7 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   for (int b = 0; b < 3; ++b) {
     const uint64_t dims[4] = {(uint64_t) h->pitch, (uint64_t) (cfg->ny + 2 * HALO), (uint64_t) cfg->nz, (uint64_t) h->N};
     const uint64_t str[3] = {(uint64_t) h->pitch * 8, (uint64_t) h->zstride * 8, (uint64_t) h->vstride * 8};
-    const uint32_t box[4] = {TILE_X + 2 * HALO, TILE_Y + 2 * HALO, 1, (uint32_t) h->N};
+    const uint32_t box[4] = {(uint32_t) tile_x(cfg->num_tracers) + 2 * HALO, (uint32_t) tile_y(cfg->num_tracers) + 2 * HALO, 1, (uint32_t) h->N};
     rc = encode_tensor_map_f64_4d(&h->tmap[b], h->q[b], dims, str, box);
     if (rc != MW_OK) { mw_dycore_destroy(h); return rc; }
   }
@@ -204,6 +217,7 @@ extern "C" int mw_dycore_destroy(mw_dycore *h) {
   for (int b = 0; b < 3; ++b) cudaFree(h->q[b]);
   cudaFree(h->flux_x); cudaFree(h->flux_y); cudaFree(h->flux_z); cudaFree(h->mult); cudaFree(h->bg);
   if (h->dev_fields_alloc) for (int f = 0; f < h->N; ++f) cudaFree(h->dev_fields[f]);
+  for (int d = 0; d < 4; ++d) { cudaFree(h->hsend[d]); cudaFree(h->hrecv[d]); cudaFree(h->msend[d]); cudaFree(h->mrecv[d]); }
   for (auto e : h->ev) cudaEventDestroy(e);
   delete h;
   return MW_OK;
@@ -251,6 +265,12 @@ extern "C" double mw_dycore_compute_time_step(const mw_dycore *h) {      // DYC:
   return cfl * fmin(fmin(h->dx, h->dy), h->dz) / maxwave;
 }
 
+extern "C" int mw_dycore_get_config(const mw_dycore *h, mw_config *out) {
+  MW_REQUIRE(h && out, "mw_dycore_get_config: null argument");
+  *out = h->cfg;
+  return MW_OK;
+}
+
 extern "C" long long mw_dycore_launch_count(const mw_dycore *h) { return h ? h->launches : 0; }
 
 extern "C" int mw_dycore_enable_timing(mw_dycore *h, int on) {
@@ -274,26 +294,104 @@ extern "C" int mw_dycore_last_timing(mw_dycore *h, float *stage_ms, int *n_stage
   return MW_OK;
 }
 
+// ---- halo exchange (replaces halo_exchange DYC:574-747 + edge_exchange DYC:830-1003 with ONE width-3 exchange) ----
+// Sends go out in the order W,E,S,N and receives are posted in the order E,W,N,S, so that with two ranks in a
+// direction (both neighbours are the same peer) the first message sent is the first one received.
+static int exchange(mw_dycore *h, double *const *send, double *const *recv, const size_t *count, cudaStream_t st) {
+  static const int send_order[4] = {0, 1, 2, 3}, recv_order[4] = {1, 0, 3, 2};
+  MW_NCCL_OK(ncclGroupStart());
+  for (int n = 0; n < 4; ++n) {
+    const int dr = recv_order[n], ds = send_order[n];
+    if (h->dir_active[dr]) MW_NCCL_OK(ncclRecv(recv[dr], count[dr], ncclDouble, h->peer[dr], h->comm->comm, st));
+    if (h->dir_active[ds]) MW_NCCL_OK(ncclSend(send[ds], count[ds], ncclDouble, h->peer[ds], h->comm->comm, st));
+  }
+  MW_NCCL_OK(ncclGroupEnd());
+  return MW_OK;
+}
+
+static int exchange_halos(mw_dycore *h, double *q, cudaStream_t st) {
+  if (!h->dir_active[0] && !h->dir_active[2]) return MW_OK;
+  const mw_config &c = h->cfg;
+  HaloParams H;
+  H.nx = c.nx; H.ny = c.ny; H.nz = c.nz; H.nvar = h->N; H.pitch = h->pitch; H.zstride = h->zstride; H.vstride = h->vstride;
+  H.q = q;
+  if (h->dir_active[0]) {
+    H.buf[0] = h->hsend[0]; H.buf[1] = h->hsend[1];
+    k_halo_x<true><<<dim3((unsigned) ((h->hcount[0] + 255) / 256), 2), 256, 0, st>>>(H);
+    h->launches++;
+  }
+  if (h->dir_active[2]) {
+    H.buf[0] = h->hsend[2]; H.buf[1] = h->hsend[3];
+    k_halo_y<true><<<dim3((unsigned) ((h->hcount[2] + 255) / 256), 2), 256, 0, st>>>(H);
+    h->launches++;
+  }
+  MW_CUDA_OK(cudaGetLastError());
+  int rc = exchange(h, h->hsend, h->hrecv, h->hcount, st);
+  if (rc != MW_OK) return rc;
+  if (h->dir_active[0]) {
+    H.buf[0] = h->hrecv[0]; H.buf[1] = h->hrecv[1];
+    k_halo_x<false><<<dim3((unsigned) ((h->hcount[0] + 255) / 256), 2), 256, 0, st>>>(H);
+    h->launches++;
+  }
+  if (h->dir_active[2]) {
+    H.buf[0] = h->hrecv[2]; H.buf[1] = h->hrecv[3];
+    k_halo_y<false><<<dim3((unsigned) ((h->hcount[2] + 255) / 256), 2), 256, 0, st>>>(H);
+    h->launches++;
+  }
+  MW_CUDA_OK(cudaGetLastError());
+  return MW_OK;
+}
+
+// boundary cells' FCT factors to the neighbouring ranks, between the stage kernel and the tracer finish
+static int exchange_mult(mw_dycore *h, cudaStream_t st) {
+  if ((!h->dir_active[0] && !h->dir_active[2]) || h->cfg.num_tracers == 0) return MW_OK;
+  const mw_config &c = h->cfg;
+  MultEdgeParams M;
+  M.nx = c.nx; M.ny = c.ny; M.nz = c.nz; M.nt = c.num_tracers; M.mult = h->mult;
+  if (h->dir_active[0]) {
+    M.out[0] = h->msend[0]; M.out[1] = h->msend[1];
+    k_mult_edge_x<<<dim3((unsigned) ((h->mcount[0] + 255) / 256), 2), 256, 0, st>>>(M);
+    h->launches++;
+  }
+  if (h->dir_active[2]) {
+    M.out[0] = h->msend[2]; M.out[1] = h->msend[3];
+    k_mult_edge_y<<<dim3((unsigned) ((h->mcount[2] + 255) / 256), 2), 256, 0, st>>>(M);
+    h->launches++;
+  }
+  MW_CUDA_OK(cudaGetLastError());
+  return exchange(h, h->msend, h->mrecv, h->mcount, st);
+}
+
 template <int NT>
 static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
+  constexpr int TILE_X = Tile<NT>::X, TILE_Y = Tile<NT>::Y;
   using C = StageCfg<NT, TILE_X, TILE_Y>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MW_CUDA_OK(cudaFuncSetAttribute(k_stage<NT, TILE_X, TILE_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int) C::SMEM_BYTES));
-    attr_set = true;
+  const size_t smem = C::smem_bytes(P.nz);
+  MW_REQUIRE(smem <= 227 * 1024, "stage kernel needs %zu bytes of shared memory (nz = %d, %d tracers): over the 227 KB limit",
+             smem, P.nz, NT);
+  static size_t attr_set = 0;
+  if (attr_set < smem) {
+    MW_CUDA_OK(cudaFuncSetAttribute(k_stage<NT, TILE_X, TILE_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    attr_set = smem;
   }
   dim3 grid((P.nx + TILE_X - 1) / TILE_X, (P.ny + TILE_Y - 1) / TILE_Y);
-  k_stage<NT, TILE_X, TILE_Y><<<grid, C::NTHR, C::SMEM_BYTES, st>>>(h->tmap[in_buf], P);
+  if (h->timing) {
+    while (h->ev.size() < (size_t) (4 + 2 * h->n_stage_timed)) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
+    cudaEventRecord(h->ev[2 + 2 * h->n_stage_timed], st);
+  }
+  k_stage<NT, TILE_X, TILE_Y><<<grid, C::NTHR, smem, st>>>(h->tmap[in_buf], P);
   MW_CUDA_OK(cudaGetLastError());
+  if (h->timing) { cudaEventRecord(h->ev[3 + 2 * h->n_stage_timed], st); h->n_stage_timed++; }
   h->launches++;
   if (NT > 0) {
+    int rc = exchange_mult(h, st);
+    if (rc != MW_OK) return rc;
     const long long ncell = (long long) P.nz * P.ny * P.nx;
     k_tracer_update<NT><<<(unsigned) ((ncell + 255) / 256), 256, 0, st>>>(P);
     MW_CUDA_OK(cudaGetLastError());
     h->launches++;
   }
-  return MW_OK;
+  return exchange_halos(h, P.qout, st);
 }
 
 template <int NT>
@@ -320,6 +418,10 @@ static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaSt
   k_coupler_to_dyn<NT><<<cgrid, 256, 0, st>>>(Q);
   MW_CUDA_OK(cudaGetLastError());
   h->launches++;
+  {
+    int rc = exchange_halos(h, h->q[0], st);
+    if (rc != MW_OK) return rc;
+  }
 
   double dt_dyn = mw_dycore_compute_time_step(h);
   const int ncycles = (int) ceil(dt_phys / dt_dyn);                        // DYC:104-108
@@ -333,10 +435,8 @@ static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaSt
       else             { in_buf = 2; P.qout = h->q[0]; P.rk_a = 1. / 3.; P.rk_b = 2. / 3.; P.rk_cdt = (2. / 3.) * dt_dyn;   P.dt_stage = (2. / 3.) * dt_dyn; }
       P.qin = h->q[in_buf];
       P.q0 = h->q[0];
-      if (h->timing) { ensure_events(4 + 2 * h->n_stage_timed); cudaEventRecord(h->ev[2 + 2 * h->n_stage_timed], st); }
       int rc = launch_stage<NT>(h, P, in_buf, st);
       if (rc != MW_OK) return rc;
-      if (h->timing) { cudaEventRecord(h->ev[3 + 2 * h->n_stage_timed], st); h->n_stage_timed++; }
     }
   }
   Q.S.qin = h->q[0];
@@ -380,8 +480,32 @@ extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields
 }
 
 extern "C" int mw_dycore_attach_comm(mw_dycore *h, mw_comm *comm) {
-  MW_REQUIRE(h, "null handle");
+  MW_REQUIRE(h && comm, "mw_dycore_attach_comm: null argument");
+  const mw_config &c = h->cfg;
+  MW_REQUIRE(comm->nranks == c.nproc_x * c.nproc_y, "communicator has %d ranks, decomposition is %d x %d", comm->nranks,
+             c.nproc_x, c.nproc_y);
+  MW_REQUIRE(comm->rank == c.py * c.nproc_x + c.px, "rank %d does not sit at (px,py) = (%d,%d)", comm->rank, c.px, c.py);
   h->comm = comm;
+  const bool sim2d = (c.ny_glob == 1);
+  auto wrap = [](int v, int n) { return (v % n + n) % n; };                 // periodic neighbours, CPL:169-179
+  h->peer[0] = c.py * c.nproc_x + wrap(c.px - 1, c.nproc_x);
+  h->peer[1] = c.py * c.nproc_x + wrap(c.px + 1, c.nproc_x);
+  h->peer[2] = wrap(c.py - 1, c.nproc_y) * c.nproc_x + c.px;
+  h->peer[3] = wrap(c.py + 1, c.nproc_y) * c.nproc_x + c.px;
+  h->dir_active[0] = h->dir_active[1] = (c.nproc_x > 1);
+  h->dir_active[2] = h->dir_active[3] = (c.nproc_y > 1) && !sim2d;
+  const size_t T = c.num_tracers;
+  for (int d = 0; d < 4; ++d) {
+    if (!h->dir_active[d]) continue;
+    h->hcount[d] = (size_t) h->N * c.nz * HALO * (d < 2 ? c.ny : c.nx);
+    h->mcount[d] = T * c.nz * (d < 2 ? c.ny : c.nx);
+    MW_CUDA_OK(cudaMalloc(&h->hsend[d], h->hcount[d] * 8));
+    MW_CUDA_OK(cudaMalloc(&h->hrecv[d], h->hcount[d] * 8));
+    if (T) {
+      MW_CUDA_OK(cudaMalloc(&h->msend[d], h->mcount[d] * 8));
+      MW_CUDA_OK(cudaMalloc(&h->mrecv[d], h->mcount[d] * 8));
+    }
+  }
   return MW_OK;
 }
 

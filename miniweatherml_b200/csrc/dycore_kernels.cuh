@@ -36,7 +36,10 @@ struct StageParams {
   double dt_stage;           // the dt handed to compute_tendencies (FCT and immersed time scale), DYC:119,136,157
   int sim2d, bc_z, enable_gravity, use_immersed;
   int wrap_x, wrap_y;        // write periodic images into the halo (single rank in that direction)
-  int lo_x_seam, hi_x_seam, lo_y_seam, hi_y_seam;   // local face 0 / nx (ny) lies on the global periodic seam
+  // FCT factors of the neighbouring rank's boundary cells ([T][nz][ny] for W/E, [T][nz][nx] for S/N); nullptr where
+  // the local boundary is the global periodic seam (or the only rank in that direction): factor 1 there, which is
+  // what the reference does with its two copies of a seam face (DYC:508-509)
+  const double *mult_W, *mult_E, *mult_S, *mult_N;
   unsigned positive_mask;    // bit tr set <=> tracer tr must stay non-negative
   int use_tma;
 };
@@ -118,8 +121,11 @@ struct StageCfg {
   static constexpr int OFF_FX = OFF_Z + 6 * TT;            // [N][XF]
   static constexpr int OFF_FY = OFF_FX + N * XF;           // [N][YF]
   static constexpr int OFF_TAB = OFF_FY + N * YF;          // int table [PER]: plane offset of each job's stencil start
-  static constexpr int OFF_END = OFF_TAB + (PER + 1) / 2;
-  static constexpr size_t SMEM_BYTES = (size_t) OFF_END * 8 + 128;   // + 2 mbarriers and 4 job counters
+  static constexpr int OFF_STG = OFF_TAB + (PER + 1) / 2;  // per-owner cp.async staging: q0 (NH), rho0', next z level (NH)
+  static constexpr int NSTG = 2 * NH + 1;
+  static constexpr int OFF_END = OFF_STG + NSTG * NTHR;    // followed by 2 mbarriers, 4 job counters and the profiles
+  static constexpr int OFF_PROF = OFF_END + 16;            // 8*nz+4 doubles (runtime)
+  static size_t smem_bytes(int nz) { return (size_t) (OFF_PROF + 8 * nz + 4) * 8; }
 };
 
 // --------------------------------------------------------------------------------------------------------
@@ -146,6 +152,8 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
   double *W = sm + C::OFF_W;
   double *E = sm + C::OFF_E;
   int *tab = reinterpret_cast<int *>(sm + C::OFF_TAB);
+  double *stg = sm + C::OFF_STG + threadIdx.x;             // my staging slots: stg[s * NTHR]
+  double *prof = sm + C::OFF_PROF;                         // background profiles, same layout as the device buffer
   double *Zs = sm + C::OFF_Z;
   double *Fx = sm + C::OFF_FX;
   double *Fy = sm + C::OFF_FY;
@@ -181,6 +189,10 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
     else { const int c = r - C::XC, yr = c / TX, x = c % TX; off = yr * PX + (x + HALO); }                 // cell y = yr-1
     tab[r] = off;
   }
+  for (int r = tid; r < 8 * P.nz + 4; r += NTHR) prof[r] = __ldg(P.hyc + r);
+  const double *s_hyc = prof, *s_hytc = prof + P.nz, *s_hye = prof + 2 * P.nz, *s_hyte = prof + 3 * P.nz + 1;
+  const double *s_ihytc = prof + 4 * P.nz + 2, *s_pcell = s_ihytc + P.nz, *s_ihyte = s_pcell + P.nz,
+               *s_pedge = s_ihyte + P.nz + 1;
   __syncthreads();
 
 #define MW_LOAD_PLANE(lev)                                                                                     \
@@ -215,7 +227,6 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
   }())
 
   double win[NH][5];      // levels c-2 .. c+2 around the level c reconstructed next
-  double nxt[NH];         // level c+3
   double vhi_prev[NH];    // high-edge value of the previously reconstructed level (L state of the next face)
   double p_hi_prev;       // its pressure (meaningful for the owner of idT only)
   double fz_lo[NH];       // flux of my variables through the low z face of the current level
@@ -225,7 +236,6 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
     const int l = v0 + v;
 #pragma unroll
     for (int s = 0; s < 5; ++s) win[v][s] = (l < N) ? MW_ZLOAD(l, s - 2) : 0.0;
-    nxt[v] = (l < N) ? MW_ZLOAD(l, 3) : 0.0;
   }
 
   MW_LOAD_PLANE(0);
@@ -235,22 +245,23 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
   // reconstruct the level the window is centred on (kz); pressures at its two faces for the idT owner
 #define MW_Z_RECON(kz)                                                                                         \
   _Pragma("unroll") for (int v = 0; v < NH; ++v) {                                                             \
+    weno5_edges(win[v][0], win[v][1], win[v][2], win[v][3], win[v][4], vlo[v], vhi[v]);                        \
+  }                                                                                                            \
+  _Pragma("unroll") for (int v = 0; v < NH; ++v) {                                                             \
     const int l = v0 + v;                                                                                      \
-    if (l < N) {                                                                                               \
-      weno5_edges(win[v][0], win[v][1], win[v][2], win[v][3], win[v][4], vlo[v], vhi[v]);                      \
+    {                                                                                                          \
       if (l == idT) {                                                                                          \
-        p_lo = eos_pressure(vlo[v], __ldg(P.hyte + (kz)), __ldg(P.ihyte + (kz)), __ldg(P.pedge + (kz)), P);    \
-        p_hi = eos_pressure(vhi[v], __ldg(P.hyte + (kz) + 1), __ldg(P.ihyte + (kz) + 1),                       \
-                            __ldg(P.pedge + (kz) + 1), P);                                                     \
+        p_lo = eos_pressure(vlo[v], s_hyte[(kz)], s_ihyte[(kz)], s_pedge[(kz)], P);                          \
+        p_hi = eos_pressure(vhi[v], s_hyte[(kz) + 1], s_ihyte[(kz) + 1], s_pedge[(kz) + 1], P);                \
       }                                                                                                        \
-    } else { vlo[v] = 0.0; vhi[v] = 0.0; }                                                                     \
+    }                                                                                                          \
   }
   // publish the Riemann inputs of a z face: Zs[q][side][TT], q: 0 full density, 1 w, 2 pressure
 #define MW_Z_PUBLISH(L, R, pL, pR, face)                                                                       \
   _Pragma("unroll") for (int v = 0; v < NH; ++v) {                                                             \
     const int l = v0 + v;                                                                                      \
     if (l == idR) {                                                                                            \
-      const double he = __ldg(P.hye + (face));                                                                 \
+      const double he = s_hye[(face)];                                                                          \
       Zs[0 * TT + oc] = L[v] + he; Zs[1 * TT + oc] = R[v] + he;                                                \
     } else if (l == idW) {                                                                                     \
       Zs[2 * TT + oc] = L[v]; Zs[3 * TT + oc] = R[v];                                                          \
@@ -273,7 +284,7 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
         const double q_up = upL ? L[v] : R[v];                                                                 \
         double f;                                                                                              \
         if (l == idR) f = m_upw;                                                                               \
-        else if (l == idT) f = m_upw * (q_up + __ldg(P.hyte + (face))) * fast_rcp(r_up);                       \
+        else if (l == idT) f = m_upw * (q_up + s_hyte[(face)]) * fast_rcp(r_up);                              \
         else f = m_upw * q_up;                                                                                 \
         if (l == idW) f += p_upw;                                                                              \
         fz[v] = f;                                                                                             \
@@ -283,16 +294,30 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
       } else fz[v] = 0.0;                                                                                      \
     }                                                                                                          \
   } while (0)
-  // shift the window up one level; afterwards it is centred on c+1 and nxt holds level c+4
+  // asynchronous 8-byte copies global -> my staging slots (cp.async; no registers held while in flight)
+#define MW_CP8(slot, gptr)                                                                                     \
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(stg + (slot) * NTHR)), "l"(gptr) : "memory")
+  // fetch level `lev` (clamped to the column, DYC:772-778) of my variables into staging slots NH+1 .. 2NH
+#define MW_Z_FETCH(lev)                                                                                        \
+  do {                                                                                                         \
+    const int lc__ = (lev) < 0 ? 0 : ((lev) >= nz ? nz - 1 : (lev));                                           \
+    _Pragma("unroll") for (int v = 0; v < NH; ++v) {                                                           \
+      const int l = min(v0 + v, N - 1);                                                                        \
+      MW_CP8(NH + 1 + v, P.qin + (long long) l * P.vstride + (long long) lc__ * P.zstride + colbase);          \
+    }                                                                                                          \
+  } while (0)
+  // shift the window up one level (afterwards centred on c+1); the new top level c+3 comes from staging
 #define MW_Z_ADVANCE(c)                                                                                        \
   _Pragma("unroll") for (int v = 0; v < NH; ++v) {                                                             \
     _Pragma("unroll") for (int s = 0; s < 4; ++s) win[v][s] = win[v][s + 1];                                   \
-    win[v][4] = nxt[v];                                                                                        \
-    const int l = v0 + v;                                                                                      \
-    nxt[v] = (l < N) ? MW_ZLOAD(l, (c) + 4) : 0.0;                                                             \
+    double t__ = stg[(NH + 1 + v) * NTHR];                                                                     \
+    if (v0 + v == idW && wall && ((c) + 3 >= nz)) t__ = 0.0;                                                   \
+    win[v][4] = t__;                                                                                           \
   }
 
   // ---- prologue: reconstruct level 0 and the bottom boundary face -----------------------------------------
+  MW_Z_FETCH(3);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   MW_Z_RECON(0);
   {
     double Lb[NH], Rb[NH];
@@ -309,7 +334,8 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
 #pragma unroll
     for (int v = 0; v < NH; ++v) vhi_prev[v] = vhi[v];
     p_hi_prev = p_hi;
-    MW_Z_ADVANCE(0);                                       // centred on level 1, nxt = level 4
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    MW_Z_ADVANCE(0);                                       // centred on level 1
     __syncthreads();
   }
 
@@ -317,7 +343,7 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
   for (int k = 0; k < nz; ++k) {
     const double *Wk = W + (k & 1) * C::SLOTP;
     int *cA = ctr + (k & 1) * 2, *cB = cA + 1;
-    const double hyc_k = __ldg(P.hyc + k), hytc_k = __ldg(P.hytc + k);
+    const double hyc_k = s_hyc[k], hytc_k = s_hytc[k];
 
     if (use_tma) {
       const uint32_t parity = (uint32_t) ((k >> 1) & 1);
@@ -335,6 +361,15 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
     }
 
     // ================= phase A =================
+    // asynchronous fetches for later in this level: the next top level of my z window and q0 of my cell
+    MW_Z_FETCH(k + 4);
+    if (P.rk_a != 0.0) {
+      const double *q0c__ = P.q0 + (long long) k * P.zstride + colbase;
+      MW_CP8(NH, q0c__);
+#pragma unroll
+      for (int v = 0; v < NH; ++v) MW_CP8(v, q0c__ + (long long) min(v0 + v, N - 1) * P.vstride);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     double Lz[NH], Rz[NH], pLz, pRz;
     if (k + 1 < nz) {
       MW_Z_RECON(k + 1);
@@ -360,27 +395,28 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
     {
       // x- and y-reconstruction jobs of level k: 64 per fetch, two per lane (same variable) for ILP
       const int per = P.sim2d ? C::XC : C::PER;
-      const double ihytc_k = __ldg(P.ihytc + k), pcell_k = __ldg(P.pcell + k);
+      const double ihytc_k = s_ihytc[k], pcell_k = s_pcell[k];
       const int lane = tid & 31;
+      // the next chunk index is fetched while the current chunk is being computed (hides the smem atomic round trip)
+      int nbase = 0;
+      if (lane == 0) nbase = atomicAdd(cA, 64);
       for (;;) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cA, 64);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        const int base = __shfl_sync(0xffffffffu, nbase, 0);
         if (base >= N * C::PERP) break;
+        if (lane == 0) nbase = atomicAdd(cA, 64);
         const int l = base / C::PERP;
         const int r0 = base - l * C::PERP + lane, r1 = r0 + 32;
         const bool a0 = r0 < per, a1 = r1 < per;
         const double *pl = Wk + l * PLANE;
-        double lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
-        if (a0) {
-          const int st = (r0 < C::XC) ? 1 : PX;
-          const double *q = pl + tab[r0];
-          weno5_edges(q[0], q[st], q[2 * st], q[3 * st], q[4 * st], lo0, hi0);
-        }
-        if (a1) {
-          const int st = (r1 < C::XC) ? 1 : PX;
-          const double *q = pl + tab[r1];
-          weno5_edges(q[0], q[st], q[2 * st], q[3 * st], q[4 * st], lo1, hi1);
+        double lo0, hi0, lo1, hi1;
+        {   // both reconstructions in one basic block so their instruction streams interleave
+          const int q0i = a0 ? r0 : 0, q1i = a1 ? r1 : 0;
+          const int st0 = (q0i < C::XC) ? 1 : PX, st1 = (q1i < C::XC) ? 1 : PX;
+          const double *qa = pl + tab[q0i], *qb = pl + tab[q1i];
+          const double a_0 = qa[0], a_1 = qa[st0], a_2 = qa[2 * st0], a_3 = qa[3 * st0], a_4 = qa[4 * st0];
+          const double b_0 = qb[0], b_1 = qb[st1], b_2 = qb[2 * st1], b_3 = qb[3 * st1], b_4 = qb[4 * st1];
+          weno5_edges(a_0, a_1, a_2, a_3, a_4, lo0, hi0);
+          weno5_edges(b_0, b_1, b_2, b_3, b_4, lo1, hi1);
         }
         if (a0) { E[(l * 2 + 0) * C::PER + r0] = lo0; E[(l * 2 + 1) * C::PER + r0] = hi0; }
         if (a1) { E[(l * 2 + 0) * C::PER + r1] = lo1; E[(l * 2 + 1) * C::PER + r1] = hi1; }
@@ -402,17 +438,6 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
     if (tid == 0) { ctr[((k + 1) & 1) * 2] = 0; ctr[((k + 1) & 1) * 2 + 1] = 0; }
 
     // ================= phase B =================
-    // q0 of my cell (plain loads: qout may alias q0 in stage 3, all reads happen before the barrier below)
-    double q0v[NH], rho0 = 0.0;
-    if (P.rk_a != 0.0) {
-      const long long cell = (long long) k * P.zstride + colbase;
-      rho0 = P.q0[cell] + hyc_k;
-#pragma unroll
-      for (int v = 0; v < NH; ++v) { const int l = v0 + v; q0v[v] = (l < N) ? P.q0[(long long) l * P.vstride + cell] : 0.0; }
-    } else {
-#pragma unroll
-      for (int v = 0; v < NH; ++v) q0v[v] = 0.0;
-    }
     {
       const int JX = C::XF, JY = P.sim2d ? 0 : C::YF;
       run_jobs(cB, JX + JY, [&](int idx) {
@@ -453,6 +478,18 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
     }
     double fz_hi[NH], zm_hi;
     MW_Z_FLUX(Lz, Rz, k + 1, fz_hi, zm_hi);
+    // my staged copies have landed (they are read by me only); in stage 3 qout aliases q0, and every read of q0
+    // is complete before any thread passes the barrier below and starts writing level k of qout
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    double q0v[NH], rho0 = 0.0;
+    if (P.rk_a != 0.0) {
+      rho0 = stg[NH * NTHR] + hyc_k;
+#pragma unroll
+      for (int v = 0; v < NH; ++v) q0v[v] = stg[v * NTHR];
+    } else {
+#pragma unroll
+      for (int v = 0; v < NH; ++v) q0v[v] = 0.0;
+    }
     __syncthreads();
 
     // ================= phase C =================
@@ -529,6 +566,8 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
 #undef MW_Z_PUBLISH
 #undef MW_Z_FLUX
 #undef MW_Z_ADVANCE
+#undef MW_Z_FETCH
+#undef MW_CP8
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -544,7 +583,7 @@ __global__ void __launch_bounds__(256) k_tracer_update(const StageParams P) {
   if (c >= ncell) return;
   const int i = (int) (c % P.nx), j = (int) ((c / P.nx) % P.ny), k = (int) (c / ((long long) P.nx * P.ny));
   const long long hcell = (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + i + HALO;
-  const double r_new = fast_rcp(P.qout[hcell] + __ldg(P.hyc + k));
+  const double rho_new = P.qout[hcell] + __ldg(P.hyc + k);
   const long long pl = (long long) P.ny * P.nx;
 #pragma unroll
   for (int tr = 0; tr < NT; ++tr) {
@@ -558,11 +597,11 @@ __global__ void __launch_bounds__(256) k_tracer_update(const StageParams P) {
     }
     if ((P.positive_mask >> tr) & 1u) {
       const double ms = Mp[0];
-      // TODO(multi-GPU): donors across a rank boundary use factor 1, like the reference's rank boundaries
-      if (fxl > 0) { if (i > 0) fxl *= Mp[-1]; }                 else if (fxl < 0) fxl *= ms;
-      if (fxh < 0) { if (i < P.nx - 1) fxh *= Mp[1]; }           else if (fxh > 0) fxh *= ms;
-      if (fyl > 0) { if (j > 0) fyl *= Mp[-P.nx]; }              else if (fyl < 0) fyl *= ms;
-      if (fyh < 0) { if (j < P.ny - 1) fyh *= Mp[P.nx]; }        else if (fyh > 0) fyh *= ms;
+      const long long eW = ((long long) tr * P.nz + k) * P.ny + j, eS = ((long long) tr * P.nz + k) * P.nx + i;
+      if (fxl > 0) { if (i > 0) fxl *= Mp[-1]; else if (P.mult_W) fxl *= P.mult_W[eW]; }             else if (fxl < 0) fxl *= ms;
+      if (fxh < 0) { if (i < P.nx - 1) fxh *= Mp[1]; else if (P.mult_E) fxh *= P.mult_E[eW]; }       else if (fxh > 0) fxh *= ms;
+      if (fyl > 0) { if (j > 0) fyl *= Mp[-P.nx]; else if (P.mult_S) fyl *= P.mult_S[eS]; }          else if (fyl < 0) fyl *= ms;
+      if (fyh < 0) { if (j < P.ny - 1) fyh *= Mp[P.nx]; else if (P.mult_N) fyh *= P.mult_N[eS]; }    else if (fyh > 0) fyh *= ms;
       if (fzl > 0) { if (k > 0) fzl *= Mp[-pl]; }                else if (fzl < 0) fzl *= ms;
       if (fzh < 0) { if (k < P.nz - 1) fzh *= Mp[pl]; }          else if (fzh > 0) fzh *= ms;
     }
@@ -570,7 +609,7 @@ __global__ void __launch_bounds__(256) k_tracer_update(const StageParams P) {
     double *qv = P.qout + (long long) (NUM_STATE + tr) * P.vstride;
     double qn = qv[hcell] + P.rk_cdt * t;
     if ((P.positive_mask >> tr) & 1u) qn = fmax(0.0, qn);
-    store_with_images(qv, P, k, j, i, qn * r_new);
+    store_with_images(qv, P, k, j, i, qn / rho_new);     // IEEE division: keeps the tracer-mass round trip unbiased
   }
 }
 
@@ -641,6 +680,62 @@ __global__ void __launch_bounds__(256) k_dyn_to_coupler(const ConvertParams Q) {
   Q.fields[2][c] = q[(long long) idV * P.vstride + h];
   Q.fields[3][c] = q[(long long) idW * P.vstride + h];
   Q.fields[4][c] = press / (rho_d * Q.R_d + rho_v * Q.R_v);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Halo strips for the x-y decomposition (replaces the pack/unpack kernels of halo_exchange, DYC:606-631,725-747;
+// width 3 instead of 2, so no edge_exchange is needed).  One launch handles both sides of a direction.
+//   dir 0: W/E strips [side][l][k][j][ii]     dir 1: S/N strips [side][l][k][jj][i]
+// --------------------------------------------------------------------------------------------------------
+struct HaloParams {
+  int nx, ny, nz, nvar, pitch;
+  long long zstride, vstride;
+  double *q;                 // haloed dycore-form buffer
+  double *buf[2];            // [side] send (pack) or receive (unpack) buffer; nullptr = skip that side
+};
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_halo_x(const HaloParams H) {
+  const long long n = (long long) H.nvar * H.nz * H.ny * HALO;
+  const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const int side = blockIdx.y;
+  if (c >= n || !H.buf[side]) return;
+  const int ii = (int) (c % HALO), j = (int) ((c / HALO) % H.ny), k = (int) ((c / (HALO * (long long) H.ny)) % H.nz);
+  const int l = (int) (c / (HALO * (long long) H.ny * H.nz));
+  // pack: W strip = interior i in [0,3), E strip = [nx-3,nx); unpack: W halo = ih in [0,3), E halo = [nx+3, nx+6)
+  const int ih = PACK ? (side == 0 ? HALO + ii : H.nx + ii) : (side == 0 ? ii : H.nx + HALO + ii);
+  double *cell = H.q + (long long) l * H.vstride + (long long) k * H.zstride + (long long) (j + HALO) * H.pitch + ih;
+  if (PACK) H.buf[side][c] = *cell; else *cell = H.buf[side][c];
+}
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_halo_y(const HaloParams H) {
+  const long long n = (long long) H.nvar * H.nz * HALO * H.nx;
+  const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const int side = blockIdx.y;
+  if (c >= n || !H.buf[side]) return;
+  const int i = (int) (c % H.nx), jj = (int) ((c / H.nx) % HALO), k = (int) ((c / ((long long) H.nx * HALO)) % H.nz);
+  const int l = (int) (c / ((long long) H.nx * HALO * H.nz));
+  const int jh = PACK ? (side == 0 ? HALO + jj : H.ny + jj) : (side == 0 ? jj : H.ny + HALO + jj);
+  double *cell = H.q + (long long) l * H.vstride + (long long) k * H.zstride + (long long) jh * H.pitch + (i + HALO);
+  if (PACK) H.buf[side][c] = *cell; else *cell = H.buf[side][c];
+}
+// boundary columns/rows of the FCT factor: out[side] = mult at i = 0 / nx-1 ([T][nz][ny]) or j = 0 / ny-1 ([T][nz][nx])
+struct MultEdgeParams {
+  int nx, ny, nz, nt;
+  const double *mult;
+  double *out[2];
+};
+__global__ void __launch_bounds__(256) k_mult_edge_x(const MultEdgeParams M) {
+  const long long n = (long long) M.nt * M.nz * M.ny, c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const int side = blockIdx.y;
+  if (c >= n || !M.out[side]) return;
+  M.out[side][c] = M.mult[c * M.nx + (side == 0 ? 0 : M.nx - 1)];
+}
+__global__ void __launch_bounds__(256) k_mult_edge_y(const MultEdgeParams M) {
+  const long long n = (long long) M.nt * M.nz * M.nx, c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const int side = blockIdx.y;
+  if (c >= n || !M.out[side]) return;
+  const long long i = c % M.nx, tk = c / M.nx;
+  M.out[side][c] = M.mult[(tk * M.ny + (side == 0 ? 0 : M.ny - 1)) * M.nx + i];
 }
 
 // kernel-level test hook for the WENO building block

@@ -150,13 +150,21 @@ def test_dycore_immersed_and_subcycling_vs_oracle(golden):
         assert relmax(out[l], ref[l]) <= TOL, (l, relmax(out[l], ref[l]))
 
 
+def exact_masses(f):
+    """Exactly rounded sums (math.fsum): total mass rho_d + sum(tracers) and each tracer mass."""
+    import math
+    tot = math.fsum(np.sum(f[[0] + list(range(5, f.shape[0]))], axis=0).ravel())
+    return np.array([tot] + [math.fsum(f[l].ravel()) for l in range(5, f.shape[0])])
+
+
 def test_mass_conservation_to_roundoff(golden):
+    """Domain mass is conserved to round-off (periodic x/y, wall z): the reference's own drift on this case is
+    5e-16 (total) / 5e-16 (vapour) after 10 steps when summed exactly."""
     g = golden("box3d_vapor_dycore5.npz")
-    p = O.make_params(int(g["nx"]), int(g["ny"]), int(g["nz"]), float(g["xlen"]), float(g["ylen"]), float(g["zlen"]), 1)
-    m0 = O.masses(p, np.ascontiguousarray(g["s0"]))
+    m0 = exact_masses(g["s0"])
     out, _ = gpu_run(g, g["s0"], 10, float(g["dt"]), 1)
-    m1 = O.masses(p, np.ascontiguousarray(out))
-    assert np.all(np.abs(m1 - m0) <= 5e-14 * np.abs(m0)), (m1 - m0) / m0
+    m1 = exact_masses(out)
+    assert np.all(np.abs(m1 - m0) <= 5e-15 * np.abs(m0)), (m1 - m0) / m0
 
 
 def test_tma_and_plain_load_paths_agree(golden, monkeypatch):

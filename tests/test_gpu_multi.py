@@ -1,0 +1,33 @@
+"""Multi-GPU parity: N-GPU runs (x-y decomposition, NCCL halos) against the single-rank CPU oracle on the same
+global grid.  Needs >= 2 GPUs; skipped otherwise (the driver's scaling run exercises the same path)."""
+import json
+import os
+import subprocess
+import sys
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _run(nproc, args, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mgpu_worker.py")] + [str(a) for a in args]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines, out.stdout[-2000:] + out.stderr[-4000:]
+    return json.loads(lines[-1])
+
+
+@pytest.mark.parametrize("nproc,nxg,nyg,T,physics", [(2, 40, 36, 1, 0), (2, 50, 1, 3, 0), (2, 36, 40, 3, 1),
+                                                     (4, 44, 40, 3, 1), (8, 64, 48, 1, 0)])
+def test_decomposition_independence(nproc, nxg, nyg, T, physics):
+    if _ngpu() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    r = _run(nproc, [nxg, nyg, T, 3, physics], 29500 + nproc)
+    assert r["ok"], r

@@ -173,3 +173,23 @@ def test_full_physics_step_vs_reference_golden(golden, name):
     for l in range(8):
         assert relmax(f[l].cpu().numpy(), g["s1"][l]) <= TOL, (l, relmax(f[l].cpu().numpy(), g["s1"][l]))
     dy.close()
+
+
+def test_init_supercell_vs_reference_initial_state(golden):
+    """mw_dycore_init_supercell (+ thermal bubble) reproduces the reference's post-init coupler state."""
+    import torch
+    import miniweatherml_b200 as mw
+    for name, T in [("config1_dycore10.npz", 3), ("box3d_vapor_dycore5.npz", 1)]:
+        g = golden(name)
+        s0 = g["s0"]
+        nz, ny, nx = s0.shape[1:]
+        cfg = mw.make_config(nx, ny, nz, float(g["xlen"]), float(g["ylen"]), float(g["zlen"]), T)
+        dy = mw.Dycore(cfg)
+        f = [torch.empty((nz, ny, nx), device="cuda", dtype=torch.float64) for _ in range(5 + T)]
+        dy.init_supercell(f)
+        mw.perturb_temperature(f[4], 0, 0, float(g["xlen"]) / nx, float(g["ylen"]) / ny, float(g["zlen"]) / nz,
+                               float(g["xlen"]), float(g["ylen"]))
+        assert relmax(dy.get_background(), g["bg"]) <= 1e-13
+        for l in range(5 + T):
+            assert relmax(f[l].cpu().numpy(), s0[l]) <= 1e-12, (name, l)
+        dy.close()

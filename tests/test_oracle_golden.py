@@ -33,12 +33,15 @@ def test_dycore_box3d(golden):
     g = golden("box3d_vapor_dycore5.npz")
     f = g["s0"].copy()
     p = params_from(g, f.shape[0] - 5)
-    m0 = O.masses(p, f)
+    import math
+    def em(a):
+        return np.array([math.fsum((a[0] + a[5]).ravel()), math.fsum(a[5].ravel())])
+    m0 = em(f)
     O.dycore_step(p, g["bg"], f, float(g["dt"]), steps=int(g["steps"]))
     for l in range(f.shape[0]):
         assert relmax(f[l], g["s1"][l]) <= 1e-13, l
-    m1 = O.masses(p, f)
-    assert np.all(np.abs(m1 - m0) <= 1e-13 * np.abs(m0))     # mass conserved to round-off (periodic x/y, wall z)
+    m1 = em(f)
+    assert np.all(np.abs(m1 - m0) <= 2e-15 * np.abs(m0))     # mass conserved to round-off (periodic x/y, wall z)
 
 
 def full_step(p, g, f, column, dt):
