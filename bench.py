@@ -85,6 +85,8 @@ class ClockSampler:
             if len(f) < 9:
                 continue
             try:
+                if float(f[3]) < 250.0:      # idle sample (before the first kernel): not "under load"
+                    continue
                 sm.append(float(f[1])); mx = float(f[2]); power.append(float(f[3]))
             except ValueError:
                 continue
@@ -216,12 +218,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                  # runs through warm-up and the timed region (same load); idle samples are dropped
     for _ in range(args.warmup):
         dy.time_step(fields, dt)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     l0 = dy.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms, n_stage = 0.0, 0
