@@ -23,7 +23,9 @@ for l in lines[start + 1:]:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.+?);", l)
     if m: instrs.append((cur, m.group(2)))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src))); hdr = rows[1]; data = rows[2:]
+rows = list(csv.reader(io.StringIO(src))); hdr = rows[1]
+ends = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
+data = [r for r in rows[2:ends[1]] if len(r) == len(hdr)]
 iI = hdr.index("Instructions Executed"); iSm = hdr.index("# Samples")
 assert len(data) == len(instrs), (len(data), len(instrs))
 byline = collections.Counter(); bylineI = collections.Counter(); tot = 0; totI = 0

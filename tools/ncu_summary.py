@@ -21,10 +21,13 @@ st = {k: float(x) for k, x in m.items() if k.startswith("smsp__average_warps_iss
 print("  stalls per issue:", ", ".join(f"{k.split('stalled_')[1].replace('_per_issue_active.ratio','')}={x:.2f}" for k, x in sorted(st.items(), key=lambda t: -t[1])[:8]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr = rows[1]; data = rows[2:]
+hdr = rows[1]
+ends = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
+data = rows[2:ends[1]]
 iS = hdr.index("Source"); iI = hdr.index("Instructions Executed")
 ops = collections.Counter(); tot = 0
 for rr in data:
+    if len(rr) <= max(iI, iS) or not rr[iI].strip().isdigit(): continue
     n = int(rr[iI]); mm = re.match(r'\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)', rr[iS]); op = mm.group(2) if mm else '?'
     ops[op] += n; tot += n
 fp = sum(n for o, n in ops.items() if o.split('.')[0] in ("DFMA", "DMUL", "DADD"))
