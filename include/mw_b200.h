@@ -74,6 +74,17 @@ int  mw_device_check(void);
 /* fills the derived constants (cv_d, gamma_d, kappa_d, C0) from R_d, cp_d, p0 exactly as DYC:1240-1247 */
 int  mw_config_defaults(mw_config *cfg);
 
+/* ---- device selection and memory (what the host-side DataManager allocates with; DM:44-59,126-195,571) ------ */
+int  mw_device_set(int ordinal);
+int  mw_device_count(int *n);
+int  mw_malloc(void **ptr, size_t bytes);
+int  mw_free(void *ptr);
+int  mw_memset(void *ptr, int byte, size_t bytes, void *stream);
+int  mw_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);     /* asynchronous */
+int  mw_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);     /* synchronises the stream */
+int  mw_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int  mw_fence(void);                                                             /* yakl::fence() */
+
 /* ---- dycore ------------------------------------------------------------------------------------------- */
 int  mw_dycore_create(const mw_config *cfg, mw_dycore **out);
 int  mw_dycore_destroy(mw_dycore *h);

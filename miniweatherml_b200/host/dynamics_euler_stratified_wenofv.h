@@ -1,0 +1,157 @@
+// modules::Dynamics_Euler_Stratified_WenoFV -- drop-in for the reference class of the same name
+// (model/modules/dynamics_euler_stratified_wenofv.h:20-2198): same init / time_step / compute_time_step signatures,
+// same option keys and DataManager entries, bodies on the C ABI of libmwb200.so (include/mw_b200.h).
+// BASELINE.json calls this class "Dynamics_Euler_Stateless"; an alias is provided below.
+#pragma once
+#include "coupler.h"
+
+namespace modules {
+class Dynamics_Euler_Stratified_WenoFV {
+ public:
+  int static constexpr ord = 5;                                     // DYC:24-28 (MW_ORD); only 5 is implemented
+  int static constexpr hs = (ord - 1) / 2;
+  int static constexpr num_state = 5;
+  int static constexpr idR = 0, idU = 1, idV = 2, idW = 3, idT = 4; // DYC:38-42
+  int static constexpr BC_PERIODIC = 0, BC_OPEN = 1, BC_WALL = 2;   // DYC:46-48
+
+ protected:
+  mw_dycore *handle = nullptr;
+  mw_config cfg;
+  real etime = 0, out_freq = -1;
+  int num_out = 0;
+  int idWV = -1;
+  std::vector<double *> field_ptrs;
+
+ public:
+  Dynamics_Euler_Stratified_WenoFV() { memset(&cfg, 0, sizeof(cfg)); }
+  ~Dynamics_Euler_Stratified_WenoFV() { if (handle) mw_dycore_destroy(handle); }
+  Dynamics_Euler_Stratified_WenoFV(Dynamics_Euler_Stratified_WenoFV const &) = delete;
+  Dynamics_Euler_Stratified_WenoFV &operator=(Dynamics_Euler_Stratified_WenoFV const &) = delete;
+
+  // DYC:70-77: dt = cfl * min(dx,dy,dz) / maxwave with cfl 0.6, maxwave 350 + 80
+  real compute_time_step(core::Coupler const &coupler) const {
+    real constexpr maxwave = 350 + 80;
+    real cfl = 0.6;
+    return cfl * std::min(std::min(coupler.get_dx(), coupler.get_dy()), coupler.get_dz()) / maxwave;
+  }
+
+  // DYC:81-198: SSPRK3 with sub-cycling; state converted from / to the coupler's (rho_d,u,v,w,T,tracer densities)
+  void time_step(core::Coupler &coupler, real &dt_phys) {
+    if (!handle) endrun("ERROR: Dynamics_Euler_Stratified_WenoFV::time_step called before init");
+    mw::check(mw_dycore_time_step(handle, field_ptrs.data(), dt_phys, nullptr), "mw_dycore_time_step");
+    etime += dt_phys;
+    if (out_freq >= 0. && etime / out_freq >= num_out + 1) {        // DYC:184-196 (output itself is out of scope)
+      yakl::fence();
+      num_out++;
+      if (coupler.is_mainproc()) std::cout << "Etime , dtphys: " << std::scientific << std::setw(10) << etime << " , " << dt_phys << std::endl;
+    }
+  }
+
+  // DYC:1197-1683
+  void init(core::Coupler &coupler) {
+    int nens = coupler.get_nens(), nx = coupler.get_nx(), ny = coupler.get_ny(), nz = coupler.get_nz();
+    if (!coupler.option_exists("R_d")) coupler.set_option<real>("R_d", 287.);
+    if (!coupler.option_exists("cp_d")) coupler.set_option<real>("cp_d", 1003.);
+    if (!coupler.option_exists("R_v")) coupler.set_option<real>("R_v", 461.);
+    if (!coupler.option_exists("cp_v")) coupler.set_option<real>("cp_v", 1859);
+    if (!coupler.option_exists("p0")) coupler.set_option<real>("p0", 1.e5);
+    if (!coupler.option_exists("grav")) coupler.set_option<real>("grav", 9.81);
+    if (!coupler.option_exists("earthrot")) coupler.set_option<real>("earthrot", 7.292115e-5);
+    auto R_d = coupler.get_option<real>("R_d"), cp_d = coupler.get_option<real>("cp_d"), R_v = coupler.get_option<real>("R_v");
+    auto cp_v = coupler.get_option<real>("cp_v"), p0 = coupler.get_option<real>("p0"), grav = coupler.get_option<real>("grav");
+    if (!coupler.option_exists("cv_d")) coupler.set_option<real>("cv_d", cp_d - R_d);
+    auto cv_d = coupler.get_option<real>("cv_d");
+    if (!coupler.option_exists("gamma_d")) coupler.set_option<real>("gamma_d", cp_d / cv_d);
+    if (!coupler.option_exists("kappa_d")) coupler.set_option<real>("kappa_d", R_d / cp_d);
+    if (!coupler.option_exists("cv_v")) coupler.set_option<real>("cv_v", R_v - cp_v);
+    auto gamma = coupler.get_option<real>("gamma_d"), kappa = coupler.get_option<real>("kappa_d");
+    if (!coupler.option_exists("C0")) coupler.set_option<real>("C0", pow(R_d * pow(p0, -kappa), gamma));
+    auto C0 = coupler.get_option<real>("C0");
+    coupler.set_option<real>("latitude", 0);
+
+    auto &dm = coupler.get_data_manager_readwrite();
+    dm.register_and_allocate<real>("density_dry", "", {nz, ny, nx, nens});
+    dm.register_and_allocate<real>("uvel", "", {nz, ny, nx, nens});
+    dm.register_and_allocate<real>("vvel", "", {nz, ny, nx, nens});
+    dm.register_and_allocate<real>("wvel", "", {nz, ny, nx, nens});
+    dm.register_and_allocate<real>("temp", "", {nz, ny, nx, nens});
+
+    int num_tracers = coupler.get_num_tracers();
+    if (num_tracers > MW_MAX_TRACERS) endrun("ERROR: too many tracers for the B200 dycore");
+    memset(&cfg, 0, sizeof(cfg));
+    auto tracer_names = coupler.get_tracer_names();
+    std::vector<unsigned char> adds_mass_host(num_tracers > 0 ? num_tracers : 1, 0);
+    idWV = -1;
+    for (int tr = 0; tr < num_tracers; ++tr) {                      // DYC:1286-1295
+      std::string desc; bool found = false, positive = false, adds_mass = false;
+      coupler.get_tracer_info(tracer_names[tr], desc, found, positive, adds_mass);
+      cfg.tracer_positive[tr] = positive; cfg.tracer_adds_mass[tr] = adds_mass; adds_mass_host[tr] = adds_mass;
+      if (tracer_names[tr] == "water_vapor") idWV = tr;
+    }
+    auto init_data = coupler.get_option<std::string>("init_data");
+    out_freq = coupler.get_option<real>("out_freq");
+    coupler.set_option<int>("idWV", idWV);
+    dm.register_and_allocate<bool>("tracer_adds_mass", "", {num_tracers});
+    if (num_tracers > 0) dm.get<bool, 1>("tracer_adds_mass").copy_from_host((bool const *) adds_mass_host.data());
+
+    coupler.set_option<bool>("use_immersed_boundaries", false);
+    dm.register_and_allocate<real>("immersed_proportion", "", {nz, ny, nx, nens});   // zero-filled on allocation
+
+    etime = 0; num_out = 0;
+
+    cfg.nx = nx; cfg.ny = ny; cfg.nz = nz; cfg.nens = nens;
+    cfg.nx_glob = (int) coupler.get_nx_glob(); cfg.ny_glob = (int) coupler.get_ny_glob();
+    cfg.i_beg = (int) coupler.get_i_beg(); cfg.j_beg = (int) coupler.get_j_beg();
+    cfg.nproc_x = coupler.get_nproc_x(); cfg.nproc_y = coupler.get_nproc_y(); cfg.px = coupler.get_px(); cfg.py = coupler.get_py();
+    cfg.xlen = coupler.get_xlen(); cfg.ylen = coupler.get_ylen(); cfg.zlen = coupler.get_zlen();
+    cfg.num_tracers = num_tracers; cfg.idWV = idWV;
+    cfg.R_d = R_d; cfg.R_v = R_v; cfg.cp_d = cp_d; cfg.p0 = p0; cfg.grav = grav; cfg.C0 = C0; cfg.gamma_d = gamma;
+    cfg.earthrot = coupler.get_option<real>("earthrot"); cfg.latitude = 0;
+    cfg.enable_gravity = coupler.get_option<bool>("enable_gravity", true) ? 1 : 0;
+    cfg.use_immersed_boundaries = 0;
+
+    if (init_data == "supercell") {                                 // DYC:1330-1337
+      coupler.add_option<int>("bc_x", BC_PERIODIC);
+      coupler.add_option<int>("bc_y", BC_PERIODIC);
+      coupler.add_option<int>("bc_z", BC_WALL);
+      coupler.add_option<real>("latitude", 0);
+    } else {
+      endrun("ERROR: init_data [" + init_data + "]: the B200 path implements the supercell test case "
+             "(thermal / city / building initialisers are SURVEY 8(f) rows, not built yet)");
+    }
+    cfg.bc_x = coupler.get_option<int>("bc_x"); cfg.bc_y = coupler.get_option<int>("bc_y"); cfg.bc_z = coupler.get_option<int>("bc_z");
+    cfg.latitude = coupler.get_option<real>("latitude");
+    mw::check(mw_dycore_create(&cfg, &handle), "mw_dycore_create");
+    if (coupler.get_nranks() > 1) mw::check(mw_dycore_attach_comm(handle, coupler.get_comm()), "mw_dycore_attach_comm");
+
+    field_ptrs.clear();
+    for (auto nm : {"density_dry", "uvel", "vvel", "wvel", "temp"}) field_ptrs.push_back(dm.get<real, 4>(nm).data());
+    for (auto &nm : tracer_names) field_ptrs.push_back(dm.get<real, 4>(nm).data());
+    // init_supercell + convert_dynamics_to_coupler (DYC:1687-1887, 1656)
+    mw::check(mw_dycore_init_supercell(handle, field_ptrs.data(), nullptr), "mw_dycore_init_supercell");
+
+    // DYC:1663-1668: background profiles visible to other modules
+    dm.register_and_allocate<real>("hy_dens_cells", "hydrostatic density cell averages", {nz, nens});
+    dm.register_and_allocate<real>("hy_dens_theta_cells", "hydrostatic density*theta cell averages", {nz, nens});
+    std::vector<double> hyc(nz), hytc(nz), hye(nz + 1), hyte(nz + 1);
+    mw::check(mw_dycore_get_background(handle, hyc.data(), hytc.data(), hye.data(), hyte.data()), "mw_dycore_get_background");
+    dm.get<real, 2>("hy_dens_cells").copy_from_host(hyc.data());
+    dm.get<real, 2>("hy_dens_theta_cells").copy_from_host(hytc.data());
+    // DYC:1671-1676 register state_flux_{x,y,z} / tracers_flux_{x,y,z}: no reader exists in the reference outside the
+    // dycore itself, and the fused stage kernel never materialises the state fluxes, so they are not
+    // allocated here (3N fields of HBM saved).
+  }
+
+  // refresh the immersed-boundary switch after another module changed "immersed_proportion" / the option
+  void update_immersed(core::Coupler &coupler) {
+    bool use = coupler.get_option<bool>("use_immersed_boundaries", false);
+    auto &dm = coupler.get_data_manager_readwrite();
+    mw::check(mw_dycore_set_immersed(handle, use ? dm.get<real, 4>("immersed_proportion").data() : nullptr), "mw_dycore_set_immersed");
+  }
+
+  mw_dycore *get_handle() const { return handle; }
+  long long get_launch_count() const { return mw_dycore_launch_count(handle); }
+  char const *dycore_name() const { return "Dynamics_Euler_Stratified_WenoFV (B200)"; }
+};
+typedef Dynamics_Euler_Stratified_WenoFV Dynamics_Euler_Stateless;      // the name BASELINE.json uses
+}  // namespace modules

@@ -1,0 +1,92 @@
+// custom_modules::Microphysics_Kessler -- drop-in for the surrogate experiment's module
+// (experiments/supercell_kessler_surrogate/custom_modules/microphysics_kessler_ponni.h:14-464): the ponni MLP
+// 5 -> 10 -> LeakyReLU(0.1) -> 4 (fp32) evaluated next to the real Kessler scheme.  Like the reference it prints
+// the mean differences (PON:266-269); unlike the reference's commented-out lines (PON:271-276) the overwrite of the
+// state by the network output is a run-time switch (`replace_with_surrogate`).
+// Weights: `nn_weights_raw` (104 little-endian fp32: W1[5][10], b1[10], W2[10][4], b2[4]) or, absent that key,
+// random-init std::mt19937(1234) uniform(-0.5,0.5) as BASELINE config 5 specifies (HDF5 is not available here, so
+// the shipped Keras .h5 cannot be read).
+#pragma once
+#include "microphysics_kessler.h"
+#include <random>
+
+namespace custom_modules {
+class Microphysics_Kessler : public modules::Microphysics_Kessler {
+ public:
+  float weights[104];
+  double scl_in[5][2], scl_out[4][2];
+  bool replace_with_surrogate = false;
+  bool use_tensor_cores = true;
+  bool print_diffs = true;
+  double *nn_out[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t nn_cells = 0;
+
+  ~Microphysics_Kessler() { for (auto p : nn_out) if (p) mw_free(p); }
+
+  void init(core::Coupler &coupler) {                               // PON:61-146
+    modules::Microphysics_Kessler::init(coupler);
+    std::string w_file, in_file, out_file;
+    if (coupler.option_exists("standalone_input_file")) {
+      YAML::Node config = YAML::LoadFile(coupler.get_option<std::string>("standalone_input_file"));
+      if (config) {
+        w_file = config["nn_weights_raw"].as<std::string>("");
+        in_file = config["nn_input_scaling"].as<std::string>("");
+        out_file = config["nn_output_scaling"].as<std::string>("");
+        replace_with_surrogate = config["replace_with_surrogate"].as<bool>(false);
+        use_tensor_cores = config["surrogate_tensor_cores"].as<bool>(true);
+      }
+    }
+    if (!w_file.empty()) {
+      std::ifstream f(w_file, std::ios::binary);
+      if (!f || !f.read((char *) weights, sizeof(weights))) endrun("ERROR: cannot read 104 fp32 weights from " + w_file);
+    } else {
+      std::mt19937 gen(1234);
+      std::uniform_real_distribution<float> dist(-0.5f, 0.5f);
+      for (auto &w : weights) w = dist(gen);
+    }
+    auto load = [](std::string const &fn, double *dst, int n, double lo, double hi) {      // PON:118-141
+      if (fn.empty()) { for (int j = 0; j < n; ++j) { dst[2 * j] = lo; dst[2 * j + 1] = hi; } return; }
+      std::ifstream f(fn);
+      if (!f) endrun("ERROR: cannot open scaling file " + fn);
+      for (int j = 0; j < 2 * n; ++j) f >> dst[j];
+    };
+    load(in_file, &scl_in[0][0], 5, 0., 1.);
+    load(out_file, &scl_out[0][0], 4, 0., 1.);
+  }
+
+  void time_step(core::Coupler &coupler, real dt) {                 // PON:149-278
+    auto &dm = coupler.get_data_manager_readwrite();
+    size_t n = (size_t) coupler.get_nz() * coupler.get_ny() * coupler.get_nx() * coupler.get_nens();
+    if (n != nn_cells) {
+      for (auto &p : nn_out) { if (p) mw_free(p); mw::check(mw_malloc((void **) &p, n * sizeof(double)), "mw_malloc"); }
+      nn_cells = n;
+    }
+    auto temp = dm.get_collapsed<real>("temp");
+    auto rho_d = dm.get_collapsed<real const>("density_dry");
+    auto rho_v = dm.get_collapsed<real>("water_vapor");
+    auto rho_c = dm.get_collapsed<real>("cloud_liquid");
+    auto rho_r = dm.get_collapsed<real>("precip_liquid");
+    mw::check(mw_surrogate_forward((long long) n, weights, &scl_in[0][0], &scl_out[0][0], temp.data(), rho_d.data(), rho_v.data(),
+                                   rho_c.data(), rho_r.data(), nn_out[0], nn_out[1], nn_out[2], nn_out[3],
+                                   use_tensor_cores ? 1 : 0, nullptr), "mw_surrogate_forward");
+    if (replace_with_surrogate) {
+      double *dst[4] = {temp.data(), rho_v.data(), rho_c.data(), rho_r.data()};
+      for (int f = 0; f < 4; ++f) mw::check(mw_memcpy_d2d(dst[f], nn_out[f], n * sizeof(double), nullptr), "mw_memcpy_d2d");
+      return;
+    }
+    modules::Microphysics_Kessler::time_step(coupler, dt);
+    if (print_diffs && coupler.is_mainproc()) {                     // PON:258-269 (host reduction: diagnostic only)
+      char const *names[4] = {"temp ", "rho_v", "rho_c", "rho_r"};
+      double *ref[4] = {temp.data(), rho_v.data(), rho_c.data(), rho_r.data()};
+      std::vector<double> a(n), b(n);
+      for (int f : {1, 2, 3, 0}) {
+        mw::check(mw_memcpy_d2h(a.data(), nn_out[f], n * 8, nullptr), "mw_memcpy_d2h");
+        mw::check(mw_memcpy_d2h(b.data(), ref[f], n * 8, nullptr), "mw_memcpy_d2h");
+        double s = 0;
+        for (size_t i = 0; i < n; ++i) s += a[i] - b[i];
+        std::cout << "Relative diff " << names[f] << ": " << s / n << "\n";
+      }
+    }
+  }
+};
+}  // namespace custom_modules
