@@ -73,9 +73,18 @@ int encode_tensor_map_f64_4d(CUtensorMap *map, const void *base, const uint64_t 
 
 using namespace mw;
 
-// tile of columns one CTA owns (two threads per column); narrower with >= 3 tracers so the CTA fits 227 KB of smem
-template <int NT> struct Tile { static constexpr int X = (NT <= 2) ? 32 : 24, Y = 8; };
-static int tile_x(int nt) { return nt <= 2 ? 32 : 24; }
+// tile of columns one CTA owns (two threads per column) and CTAs resident per SM.  Variant 0: 32 x 8 (24 x 8 with >= 3
+// tracers so the CTA fits 227 KB of smem), one CTA per SM.  Variant 1: 16 x 8, two CTAs per SM, so that one CTA's
+// integer-heavy update phase overlaps the other's FP64-heavy reconstruction phase.
+template <int NT, int VAR> struct Tile {
+  static constexpr int X = VAR == 1 ? 16 : ((NT <= 1) ? 32 : 24), Y = 8, MINB = VAR == 1 ? 2 : 1;
+};
+static int tile_variant(int nt) {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("MW_TILE_VARIANT"); v = e ? atoi(e) : 0; }
+  return (nt <= 1) ? v : 0;
+}
+static int tile_x(int nt) { return tile_variant(nt) == 1 ? 16 : (nt <= 1 ? 32 : 24); }
 static int tile_y(int) { return 8; }
 
 struct mw_dycore {
@@ -362,16 +371,16 @@ static int exchange_mult(mw_dycore *h, cudaStream_t st) {
   return exchange(h, h->msend, h->mrecv, h->mcount, st);
 }
 
-template <int NT>
-static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
-  constexpr int TILE_X = Tile<NT>::X, TILE_Y = Tile<NT>::Y;
+template <int NT, int VAR>
+static int launch_stage_v(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
+  constexpr int TILE_X = Tile<NT, VAR>::X, TILE_Y = Tile<NT, VAR>::Y, MINB = Tile<NT, VAR>::MINB;
   using C = StageCfg<NT, TILE_X, TILE_Y>;
   const size_t smem = C::smem_bytes(P.nz);
   MW_REQUIRE(smem <= 227 * 1024, "stage kernel needs %zu bytes of shared memory (nz = %d, %d tracers): over the 227 KB limit",
              smem, P.nz, NT);
   static size_t attr_set = 0;
   if (attr_set < smem) {
-    MW_CUDA_OK(cudaFuncSetAttribute(k_stage<NT, TILE_X, TILE_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    MW_CUDA_OK(cudaFuncSetAttribute(k_stage<NT, TILE_X, TILE_Y, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     attr_set = smem;
   }
   dim3 grid((P.nx + TILE_X - 1) / TILE_X, (P.ny + TILE_Y - 1) / TILE_Y);
@@ -379,7 +388,7 @@ static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStre
     while (h->ev.size() < (size_t) (4 + 2 * h->n_stage_timed)) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
     cudaEventRecord(h->ev[2 + 2 * h->n_stage_timed], st);
   }
-  k_stage<NT, TILE_X, TILE_Y><<<grid, C::NTHR, smem, st>>>(h->tmap[in_buf], P);
+  k_stage<NT, TILE_X, TILE_Y, MINB><<<grid, C::NTHR, smem, st>>>(h->tmap[in_buf], P);
   MW_CUDA_OK(cudaGetLastError());
   if (h->timing) { cudaEventRecord(h->ev[3 + 2 * h->n_stage_timed], st); h->n_stage_timed++; }
   h->launches++;
@@ -392,6 +401,11 @@ static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStre
     h->launches++;
   }
   return exchange_halos(h, P.qout, st);
+}
+template <int NT>
+static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
+  if constexpr (NT <= 1) { if (tile_variant(NT) == 1) return launch_stage_v<NT, 1>(h, P, in_buf, st); }
+  return launch_stage_v<NT, 0>(h, P, in_buf, st);
 }
 
 template <int NT>
