@@ -2,6 +2,7 @@
 // scratch, the background profiles and the TMA descriptors, and sequences the kernels of one time_step
 // (reference: model/modules/dynamics_euler_stratified_wenofv.h:81-198).
 #include "dycore_kernels.cuh"
+#include "stage_ws.cuh"
 #include "comm.cuh"
 #include <cmath>
 #include <cstring>
@@ -79,12 +80,19 @@ using namespace mw;
 template <int NT, int VAR> struct Tile {
   static constexpr int X = VAR == 1 ? 16 : ((NT <= 1) ? 32 : 24), Y = 8, MINB = VAR == 1 ? 2 : 1;
 };
+// Variant 2: warp-specialised kernel (stage_ws.cuh), 16 x 8 tile, reconstruction and update warps run concurrently.
 static int tile_variant(int nt) {
   static int v = -1;
-  if (v < 0) { const char *e = getenv("MW_TILE_VARIANT"); v = e ? atoi(e) : 0; }
+  if (v < 0) {
+    const char *e = getenv("MW_TILE_VARIANT");
+    v = e ? atoi(e) : 0;
+    const char *t = getenv("MW_NO_TMA");
+    if (t && atoi(t) != 0) v = 0;                           // the plain-load path exists in the phase kernel only
+  }
+  if (v == 2) return nt <= 3 ? 2 : 0;
   return (nt <= 1) ? v : 0;
 }
-static int tile_x(int nt) { return tile_variant(nt) == 1 ? 16 : (nt <= 1 ? 32 : 24); }
+static int tile_x(int nt) { return tile_variant(nt) >= 1 ? 16 : (nt <= 1 ? 32 : 24); }
 static int tile_y(int) { return 8; }
 
 struct mw_dycore {
@@ -371,6 +379,7 @@ static int exchange_mult(mw_dycore *h, cudaStream_t st) {
   return exchange(h, h->msend, h->mrecv, h->mcount, st);
 }
 
+static int finish_stage(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st);
 template <int NT, int VAR>
 static int launch_stage_v(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
   constexpr int TILE_X = Tile<NT, VAR>::X, TILE_Y = Tile<NT, VAR>::Y, MINB = Tile<NT, VAR>::MINB;
@@ -392,18 +401,48 @@ static int launch_stage_v(mw_dycore *h, const StageParams &P, int in_buf, cudaSt
   MW_CUDA_OK(cudaGetLastError());
   if (h->timing) { cudaEventRecord(h->ev[3 + 2 * h->n_stage_timed], st); h->n_stage_timed++; }
   h->launches++;
-  if (NT > 0) {
+  return finish_stage(h, P, NT, st);
+}
+// tracer finish (FCT-scaled divergence, RK, clip) and the halo exchange of the new state
+static int finish_stage(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st) {
+  if (nt > 0) {
     int rc = exchange_mult(h, st);
     if (rc != MW_OK) return rc;
     const long long ncell = (long long) P.nz * P.ny * P.nx;
-    k_tracer_update<NT><<<(unsigned) ((ncell + 255) / 256), 256, 0, st>>>(P);
+    const unsigned g = (unsigned) ((ncell + 255) / 256);
+    switch (nt) {
+      case 1: k_tracer_update<1><<<g, 256, 0, st>>>(P); break;
+      case 2: k_tracer_update<2><<<g, 256, 0, st>>>(P); break;
+      case 3: k_tracer_update<3><<<g, 256, 0, st>>>(P); break;
+      case 4: k_tracer_update<4><<<g, 256, 0, st>>>(P); break;
+    }
     MW_CUDA_OK(cudaGetLastError());
     h->launches++;
   }
   return exchange_halos(h, P.qout, st);
 }
 template <int NT>
+static int launch_stage_ws(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
+  using C = WsCfg<NT, 16, 8>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MW_CUDA_OK(cudaFuncSetAttribute(k_stage_ws<NT, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
+    attr_set = true;
+  }
+  dim3 grid((P.nx + 15) / 16, (P.ny + 7) / 8);
+  if (h->timing) {
+    while (h->ev.size() < (size_t) (4 + 2 * h->n_stage_timed)) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
+    cudaEventRecord(h->ev[2 + 2 * h->n_stage_timed], st);
+  }
+  k_stage_ws<NT, 16, 8><<<grid, C::NTHR, C::SMEM, st>>>(h->tmap[in_buf], P);
+  MW_CUDA_OK(cudaGetLastError());
+  if (h->timing) { cudaEventRecord(h->ev[3 + 2 * h->n_stage_timed], st); h->n_stage_timed++; }
+  h->launches++;
+  return finish_stage(h, P, NT, st);
+}
+template <int NT>
 static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
+  if constexpr (NT <= 3) { if (tile_variant(NT) == 2) return launch_stage_ws<NT>(h, P, in_buf, st); }
   if constexpr (NT <= 1) { if (tile_variant(NT) == 1) return launch_stage_v<NT, 1>(h, P, in_buf, st); }
   return launch_stage_v<NT, 0>(h, P, in_buf, st);
 }
