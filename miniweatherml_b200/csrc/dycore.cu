@@ -85,7 +85,7 @@ static int tile_variant(int nt) {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("MW_TILE_VARIANT");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : 2;                               // default: the warp-specialised kernel
     const char *t = getenv("MW_NO_TMA");
     if (t && atoi(t) != 0) v = 0;                           // the plain-load path exists in the phase kernel only
   }

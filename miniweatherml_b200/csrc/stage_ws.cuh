@@ -21,21 +21,24 @@ struct WsCfg {
   static constexpr int N = NUM_STATE + NT;
   static constexpr int TX = TX_, TY = TY_;
   static constexpr int TT = TX * TY;                       // owned columns
-  static constexpr int NR = 2 * TT;                        // reconstruction threads (two per column)
+  static constexpr int NRO = 2 * TT;                       // reconstruction threads that own a z window (two per column)
+  static constexpr int NRH = TT;                           // reconstruction helper threads (x/y jobs only)
+  static constexpr int NR = NRO + NRH;
   static constexpr int NU = TT;                            // update threads (one per column)
   static constexpr int NTHR = NR + NU;
-  static constexpr int NRW = NR / 32, NUW = NU / 32;
   static constexpr int NH = (N + 1) / 2;                   // variables per z-owner thread
   static constexpr int PX = TX + 2 * HALO, PY = TY + 2 * HALO, PLANE = PX * PY;
   static constexpr int SLOT = N * PLANE;
   static constexpr int SLOTP = ((SLOT + 15) / 16) * 16;    // TMA destinations stay 128-byte aligned
   static constexpr int NSLOT = (N <= 6) ? 4 : 3;           // plane ring
   static constexpr int XC = TY * (TX + 2), YC = (TY + 2) * TX, XF = TY * (TX + 1), YF = (TY + 1) * TX;
-  static constexpr int PER = XC + YC;                      // reconstruction jobs per variable and level
+  static constexpr int PER = XC + YC;                      // x/y reconstruction jobs per variable and level
   static constexpr int JT = N * PER;
-  static constexpr int ROUNDS = (JT + NR - 1) / NR;
-  static constexpr int LEAD = (PER / NR) * NR;             // (rho*theta)' jobs scheduled first, in whole rounds
-  static constexpr int LEAD_ROUNDS = LEAD / NR;
+  // balanced static schedule: every reconstruction thread does QH reconstructions per level; an owner spends NH of
+  // them on its z window, so it takes QO = QH - NH x/y jobs and a helper takes QH
+  static constexpr int QH = (JT + NH * NRO + NR - 1) / NR;
+  static constexpr int QO = QH - NH;
+  static_assert(QO >= 1 && NR * QO + NRH * (QH - QO) >= JT, "job schedule does not cover the level");
   static constexpr int ESZ = (N + 1) * 2 * PER;            // one E buffer: [N+1][2][PER], variable N = pressure
   static constexpr int ZSZ = 2 * (N + 1) * TT;             // one Z buffer: [N+1][2][TT]
   static constexpr int OFF_W = 0;
@@ -43,13 +46,13 @@ struct WsCfg {
   static constexpr int OFF_Z = OFF_E + 2 * ESZ;
   static constexpr int OFF_FX = OFF_Z + 2 * ZSZ;           // [N][XF]
   static constexpr int OFF_FY = OFF_FX + N * XF;           // [N][YF]
-  static constexpr int OFF_STG = OFF_FY + N * YF;          // R: cp.async staging of the next window level [NH][NR]
-  static constexpr int OFF_DESC = OFF_STG + NH * NR;       // unsigned [ROUNDS][NR]
-  static constexpr int OFF_BAR = OFF_DESC + (ROUNDS * NR + 1) / 2;   // NSLOT tma + 2 full + 2 empty mbarriers
+  static constexpr int OFF_STG = OFF_FY + N * YF;          // owners: cp.async staging of the next window level [NH][NRO]
+  static constexpr int OFF_DESC = OFF_STG + NH * NRO;      // unsigned [QH][NR]
+  static constexpr int OFF_BAR = OFF_DESC + (QH * NR + 1) / 2;   // NSLOT tma + 2 full + 2 empty mbarriers
   static constexpr size_t SMEM = (size_t) (OFF_BAR + NSLOT + 4) * 8;
   static constexpr unsigned D_YSTR = 1u << 27, D_IST = 1u << 28, D_VALID = 1u << 29;
   static_assert(N * PLANE < (1 << 13) && ESZ < (1 << 14), "descriptor fields too narrow");
-  static_assert(NR % 32 == 0 && NU % 32 == 0, "whole warps per role");
+  static_assert(NRO % 128 == 0 && NRH % 128 == 0 && NU % 128 == 0, "whole warpgroups per role");
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -73,10 +76,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 }
 
 template <int NT, int TX, int TY>
-__global__ void __launch_bounds__(3 * TX * TY, 1)
+__global__ void __launch_bounds__(4 * TX * TY, 1)
 k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
   using C = WsCfg<NT, TX, TY>;
-  constexpr int N = C::N, NH = C::NH, TT = C::TT, PX = C::PX, PLANE = C::PLANE, NR = C::NR, PER = C::PER, NSLOT = C::NSLOT;
+  constexpr int N = C::N, NH = C::NH, TT = C::TT, PX = C::PX, PLANE = C::PLANE, NR = C::NR, NRO = C::NRO, PER = C::PER, NSLOT = C::NSLOT;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double *sm = reinterpret_cast<double *>(smem_raw);
   double *W = sm + C::OFF_W;
@@ -106,15 +109,10 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
 
   if (tid < NR) {
     // =====================================================================================================
-    // R: reconstruction warps
+    // R: reconstruction warps (owners of a z window: tid < NRO; helpers: x/y jobs only)
     // =====================================================================================================
-    double *stg = sm + C::OFF_STG + tid;                    // my staging slots: stg[v * NR]
+    const bool owner = tid < NRO;
     unsigned *rdesc = reinterpret_cast<unsigned *>(sm + C::OFF_DESC) + tid;   // my job descriptors: rdesc[m * NR]
-    const int oc = tid % TT, oh = tid / TT;
-    const int oy = oc / TX, ox = oc % TX;
-    const int v0 = oh * NH;
-    const int gi = i0 + ox, gj = j0 + oy;
-    const long long colbase = (long long) (min(gj, P.ny - 1) + HALO) * P.pitch + (min(gi, P.nx - 1) + HALO);
 
     if (tid == 0) {                                         // first planes of the ring
       for (int lev = 0; lev < NSLOT - 1 && lev < nz; ++lev) {
@@ -122,15 +120,15 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
         tma_load_4d(W + lev * C::SLOTP, &tmap, &tma_bar[lev], i0, j0, lev, 0);
       }
     }
-    // static schedule of my x/y reconstruction jobs (see StageCfg in dycore_kernels.cuh for the ordering)
-    for (int m = 0; m < C::ROUNDS; ++m) {
-      const int j = tid + NR * m;
-      bool valid = j < C::JT;
-      int l, r;
-      if (j < C::LEAD) { l = idT; r = j; }
-      else if (j < C::LEAD + (N - 1) * PER) { const int q = j - C::LEAD, lp = q / PER; r = q - lp * PER; l = lp < idT ? lp : lp + 1; }
-      else { l = idT; r = C::LEAD + (j - C::LEAD - (N - 1) * PER); }
-      if (!valid) { l = 0; r = 0; }
+    // static schedule of my x/y reconstruction jobs: rounds [0, QO) are shared by all R threads, rounds [QO, QH) belong
+    // to the helpers.  Jobs are ordered (rho*theta)' first (those also evaluate the edge pressures), then the others.
+    for (int m = 0; m < C::QH; ++m) {
+      int j = -1;
+      if (m < C::QO) j = m * NR + tid;
+      else if (!owner) j = C::QO * NR + (m - C::QO) * C::NRH + (tid - NRO);
+      bool valid = j >= 0 && j < C::JT;
+      int l = 0, r = 0;
+      if (valid) { const int lp = j / PER; r = j - lp * PER; l = lp == 0 ? idT : (lp <= idT ? lp - 1 : lp); }
       const bool isy = r >= C::XC;
       if (isy && P.sim2d) valid = false;
       int off;
@@ -139,6 +137,15 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
       rdesc[m * NR] = (unsigned) (l * PLANE + off) | ((unsigned) (l * 2 * PER + r) << 13) | (isy ? C::D_YSTR : 0u) |
                       (l == idT ? C::D_IST : 0u) | (valid ? C::D_VALID : 0u);
     }
+    auto signal_full = [&](int lev) { mbar_arrive(&full_bar[buf_of(lev)]); };      // release: my E/Z writes are visible
+
+    // ---- owner state (dead registers in the helper warps) -----------------------------------------------------
+    double *stg = sm + C::OFF_STG + (owner ? tid : 0);      // my staging slots: stg[v * NRO]
+    const int oc = tid % TT, oh = owner ? tid / TT : 0;
+    const int oy = oc / TX, ox = oc % TX;
+    const int v0 = oh * NH;
+    const int gi = i0 + ox, gj = j0 + oy;
+    const long long colbase = (long long) (min(gj, P.ny - 1) + HALO) * P.pitch + (min(gi, P.nx - 1) + HALO);
 
     auto zload = [&](int l, int lev) -> double {            // DYC:752-781: copy the nearest interior cell, wall zeroes w
       const int lc = lev < 0 ? 0 : (lev >= nz ? nz - 1 : lev);
@@ -152,18 +159,11 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
       for (int v = 0; v < NH; ++v) {
         const int l = min(v0 + v, N - 1);
         const double *g = P.qin + (long long) l * P.vstride + (long long) lc * P.zstride + colbase;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(stg + v * NR)), "l"(g) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(stg + v * NRO)), "l"(g) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-
     double win[NH][5], vlo[NH], vhi[NH], vhi_prev[NH], p_lo = 0.0, p_hi = 0.0, p_hi_prev = 0.0;
-#pragma unroll
-    for (int v = 0; v < NH; ++v) {
-      const int l = v0 + v;
-#pragma unroll
-      for (int s = 0; s < 5; ++s) win[v][s] = (l < N) ? zload(l, s - 2) : 0.0;
-    }
     auto zrecon = [&](int kz) {                             // level kz = the one the window is centred on
 #pragma unroll
       for (int v = 0; v < NH; ++v) weno5_edges(win[v][0], win[v][1], win[v][2], win[v][3], win[v][4], vlo[v], vhi[v]);
@@ -180,7 +180,7 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
       for (int v = 0; v < NH; ++v) {
 #pragma unroll
         for (int s = 0; s < 4; ++s) win[v][s] = win[v][s + 1];
-        double t = stg[v * NR];
+        double t = stg[v * NRO];
         if (v0 + v == idW && wall && (c + 3 >= nz)) t = 0.0;
         win[v][4] = t;
       }
@@ -194,12 +194,17 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
         if (l == idT) { Z[(2 * N) * TT + oc] = pL; Z[(2 * N + 1) * TT + oc] = pR; }
       }
     };
-    auto signal_full = [&](int lev) { mbar_arrive(&full_bar[buf_of(lev)]); };      // release: my E/Z writes are visible
 
     // ---- prologue: level 0 and the bottom boundary face ("level" -1, buffer 1) ------------------------------
-    zfetch(3);
-    zrecon(0);
-    {
+    if (owner) {
+#pragma unroll
+      for (int v = 0; v < NH; ++v) {
+        const int l = v0 + v;
+#pragma unroll
+        for (int s = 0; s < 5; ++s) win[v][s] = (l < N) ? zload(l, s - 2) : 0.0;
+      }
+      zfetch(3);
+      zrecon(0);
       double Lb[NH], Rb[NH];
 #pragma unroll
       for (int v = 0; v < NH; ++v) {
@@ -208,29 +213,31 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
         Lb[v] = Rb[v];                                      // DYC:1020-1038: both sides mirrored from the interior
       }
       zpublish(sm + C::OFF_Z + C::ZSZ, Lb, Rb, p_lo, p_lo);
-      signal_full(-1);
 #pragma unroll
       for (int v = 0; v < NH; ++v) vhi_prev[v] = vhi[v];
       p_hi_prev = p_hi;
       zadvance(0);                                          // centred on level 1
     }
+    signal_full(-1);                                        // the hand-off counts every R thread
 
+    const int njobs = owner ? C::QO : C::QH;
+#pragma unroll 1
     for (int k = 0; k < nz; ++k) {
       const int b = k & 1;
       double *E = sm + C::OFF_E + b * C::ESZ;
       // buffers b are free once U has finished level k-2 (the prologue for k = 1); its plane slot is refilled
       if (k >= 1) mbar_wait_spin(&empty_bar[b], par_of(k - 2));
-      if (tid == 0) {
-        const int lev = k + NSLOT - 2;
-        if (k >= 1 && lev < nz) {
-          fence_proxy_async();
-          mbar_expect_tx(&tma_bar[lev % NSLOT], (uint32_t) (C::SLOT * 8));
-          tma_load_4d(W + (lev % NSLOT) * C::SLOTP, &tmap, &tma_bar[lev % NSLOT], i0, j0, lev, 0);
+      if (owner) {
+        if (tid == 0) {
+          const int lev = k + NSLOT - 2;
+          if (k >= 1 && lev < nz) {
+            fence_proxy_async();
+            mbar_expect_tx(&tma_bar[lev % NSLOT], (uint32_t) (C::SLOT * 8));
+            tma_load_4d(W + (lev % NSLOT) * C::SLOTP, &tmap, &tma_bar[lev % NSLOT], i0, j0, lev, 0);
+          }
         }
-      }
-      zfetch(k + 4);
-      // z reconstruction of level k+1 -> face k+1/2
-      {
+        zfetch(k + 4);
+        // z reconstruction of level k+1 -> face k+1/2
         double Lz[NH], Rz[NH], pLz, pRz;
         if (k + 1 < nz) {
           zrecon(k + 1);
@@ -251,44 +258,54 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
         for (int v = 0; v < NH; ++v) vhi_prev[v] = vhi[v];
         p_hi_prev = p_hi;
       }
-      // x / y reconstruction jobs of level k
-      mbar_wait_spin(&tma_bar[k % NSLOT], (uint32_t) ((k / NSLOT) & 1));
+      // ---- x / y reconstruction jobs of level k from my schedule: pairs (two interleaved for ILP), then an odd one ----
       {
         const double *Wk = W + (k % NSLOT) * C::SLOTP;
         const double hytc_k = __ldg(P.hytc + k), ihytc_k = __ldg(P.ihytc + k), pcell_k = __ldg(P.pcell + k);
+        mbar_wait_spin(&tma_bar[k % NSLOT], (uint32_t) ((k / NSLOT) & 1));
         constexpr int EP = (N * 2 - idT * 2) * PER;         // from a (rho*theta)' edge value to its pressure slot
-#pragma unroll
-        for (int m = 0; m < C::ROUNDS; m += 2) {
-          const bool has1 = (m + 1 < C::ROUNDS);
-          const unsigned d0 = rdesc[m * NR], d1 = has1 ? rdesc[(m + 1) * NR] : 0u;
+        constexpr unsigned PV = C::D_IST | C::D_VALID;
+        int m = 0;
+#pragma unroll 1
+        for (; m + 1 < njobs; m += 2) {
+          const unsigned d0 = rdesc[m * NR], d1 = rdesc[(m + 1) * NR];
           const double *qa = Wk + (d0 & 0x1fffu), *qb = Wk + (d1 & 0x1fffu);
           const int st0 = (d0 & C::D_YSTR) ? PX : 1, st1 = (d1 & C::D_YSTR) ? PX : 1;
-          double lo0, hi0, lo1 = 0.0, hi1 = 0.0;
+          double lo0, hi0, lo1, hi1;
           {
             const double a_0 = qa[0], a_1 = qa[st0], a_2 = qa[2 * st0], a_3 = qa[3 * st0], a_4 = qa[4 * st0];
-            if (has1) {
-              const double b_0 = qb[0], b_1 = qb[st1], b_2 = qb[2 * st1], b_3 = qb[3 * st1], b_4 = qb[4 * st1];
-              weno5_edges(a_0, a_1, a_2, a_3, a_4, lo0, hi0);
-              weno5_edges(b_0, b_1, b_2, b_3, b_4, lo1, hi1);
-            } else {
-              weno5_edges(a_0, a_1, a_2, a_3, a_4, lo0, hi0);
-            }
+            const double b_0 = qb[0], b_1 = qb[st1], b_2 = qb[2 * st1], b_3 = qb[3 * st1], b_4 = qb[4 * st1];
+            weno5_edges(a_0, a_1, a_2, a_3, a_4, lo0, hi0);
+            weno5_edges(b_0, b_1, b_2, b_3, b_4, lo1, hi1);
           }
           double *e0 = E + ((d0 >> 13) & 0x3fffu), *e1 = E + ((d1 >> 13) & 0x3fffu);
           if (d0 & C::D_VALID) { e0[0] = lo0; e0[PER] = hi0; }
-          if (has1 && (d1 & C::D_VALID)) { e1[0] = lo1; e1[PER] = hi1; }
-          if (m < C::LEAD_ROUNDS || (m * NR + NR > C::LEAD + (N - 1) * PER && (d0 & C::D_IST) && (d0 & C::D_VALID))) {
+          if (d1 & C::D_VALID) { e1[0] = lo1; e1[PER] = hi1; }
+          if ((d0 & PV) == PV) {
             e0[EP] = eos_pressure(lo0, hytc_k, ihytc_k, pcell_k, P);
             e0[EP + PER] = eos_pressure(hi0, hytc_k, ihytc_k, pcell_k, P);
           }
-          if (has1 && (m + 1 < C::LEAD_ROUNDS || ((m + 1) * NR + NR > C::LEAD + (N - 1) * PER && (d1 & C::D_IST) && (d1 & C::D_VALID)))) {
+          if ((d1 & PV) == PV) {
             e1[EP] = eos_pressure(lo1, hytc_k, ihytc_k, pcell_k, P);
             e1[EP + PER] = eos_pressure(hi1, hytc_k, ihytc_k, pcell_k, P);
           }
         }
+        if (m < njobs) {
+          const unsigned d0 = rdesc[m * NR];
+          const double *qa = Wk + (d0 & 0x1fffu);
+          const int st0 = (d0 & C::D_YSTR) ? PX : 1;
+          double lo0, hi0;
+          weno5_edges(qa[0], qa[st0], qa[2 * st0], qa[3 * st0], qa[4 * st0], lo0, hi0);
+          double *e0 = E + ((d0 >> 13) & 0x3fffu);
+          if (d0 & C::D_VALID) { e0[0] = lo0; e0[PER] = hi0; }
+          if ((d0 & PV) == PV) {
+            e0[EP] = eos_pressure(lo0, hytc_k, ihytc_k, pcell_k, P);
+            e0[EP + PER] = eos_pressure(hi0, hytc_k, ihytc_k, pcell_k, P);
+          }
+        }
       }
       signal_full(k);
-      zadvance(k + 1);
+      if (owner) zadvance(k + 1);
     }
   } else {
     // =====================================================================================================

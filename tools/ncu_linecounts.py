@@ -28,7 +28,7 @@ data = [r for r in rows[2:ends[1]] if len(r) == len(hdr)]
 iI = hdr.index("Instructions Executed"); iSm = hdr.index("# Samples")
 agg = collections.defaultdict(lambda: [0, 0, collections.Counter()])
 for ((f, ln), txt), r in zip(instrs, data):
-    if not f.startswith("dycore_kernels") or not (lo <= ln <= hi): continue
+    if not f.startswith(os.environ.get("MW_SRC", "dycore_kernels")) or not (lo <= ln <= hi): continue
     mo = re.match(r'\s*(@!?U?P[T\d]+\s+)?([A-Z0-9_.]+)', txt); op = mo.group(2) if mo else '?'
     a = agg[ln]; a[0] += int(r[iI]); a[1] += int(r[iSm]); a[2][op.split('.')[0]] += int(r[iI])
 for ln, a in sorted(agg.items(), key=lambda t: -t[1][0])[:25]:

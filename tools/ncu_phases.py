@@ -34,7 +34,7 @@ agg = collections.defaultdict(lambda: [0, 0, 0, 0, collections.Counter()])
 tot = [0, 0, 0]
 for ((f, ln), txt), r in zip(instrs, data):
     name = "other"
-    if f.startswith("dycore_kernels"):
+    if f.startswith(os.environ.get("MW_SRC", "dycore_kernels")):
         for n, lo, hi in ranges:
             if lo <= ln <= hi: name = n; break
     else:
