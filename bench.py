@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -85,7 +85,7 @@ class ClockSampler:
             if len(f) < 9:
                 continue
             try:
-                if float(f[3]) < 250.0:      # idle sample (before the first kernel): not "under load"
+                if float(f[1]) < 600.0:      # idle sample (SM clock parked at ~120 MHz before the first kernel): not "under load"
                     continue
                 sm.append(float(f[1])); mx = float(f[2]); power.append(float(f[3]))
             except ValueError:
@@ -273,13 +273,22 @@ def main():
         k_ms = s_ms / max(s_n, 1)
         achieved = alg_bytes_per_launch / (k_ms * 1e-3) / 1e9
         traffic = None
-        fp64_pct = None
+        fp64 = None
         pj = os.path.join(ROOT, "profiles", "stage_kernel_bench.json")
         if os.path.exists(pj):
             try:
                 pr = json.load(open(pj))
                 traffic = pr.get("dram_bytes_per_launch")
-                fp64_pct = pr.get("fp64_pipe_pct_of_peak")
+                # FP64-pipe view of the same launch: fp64 instructions per cell-stage counted by ncu (committed capture)
+                # x cells / live CUDA-event duration, against the DFMA issue rate measured by tools/fp64_peak.cu
+                fi = pr.get("fp64_thread_instr_per_cell_stage")
+                pk = pr.get("fp64_peak_thread_instr_per_s")
+                if fi and pk:
+                    ach = fi * cells_loc / (k_ms * 1e-3)
+                    fp64 = {"bound": "fp64-pipe", "achieved": ach / 1e12, "peak": pk / 1e12, "unit": "T fp64-instr/s",
+                            "frac": ach / pk, "fp64_instr_per_cell_stage": fi,
+                            "ncu_pipe_fp64_cycles_active_pct": pr.get("ncu_pipe_fp64_cycles_active_pct"),
+                            "peak_source": "measured DFMA issue rate (tools/fp64_peak.cu, profiles/r01a_device_peaks.jsonl)"}
             except Exception:
                 pass
         line = {"metric": "cell-updates/s per SSPRK3 step", "value": value, "unit": "cell-updates/s", "n_gpus": world,
@@ -296,11 +305,11 @@ def main():
                         "api": "mw_dycore_time_step_host (pinned host buffers)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "k_stage", "kernel_ms": k_ms, "peak_source": peak_src,
+                             "traffic": traffic, "kernel": "k_stage_ws", "kernel_ms": k_ms, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                             "note": "the fused stage kernel is FP64-pipe-bound, not HBM-bound (see DESIGN.md); "
-                                     "fp64_pipe_pct_of_peak from the committed ncu capture",
-                             "fp64_pipe_pct_of_peak": fp64_pct,
+                             "note": "the fused stage kernel is FP64-pipe-bound, not HBM-bound (DESIGN.md section 4): "
+                                     "the binding roofline is reported under fp64_pipe",
+                             "fp64_pipe": fp64,
                              "whole_step_frac": value / world * BYTES_PER_CELL_UPDATE / 1e9 / peak}}
         if not args.no_cpu_baseline:
             try:
