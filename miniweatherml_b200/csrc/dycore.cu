@@ -5,6 +5,7 @@
 #include "stage_ws.cuh"
 #include "comm.cuh"
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 #include <cstdlib>
@@ -120,6 +121,10 @@ struct mw_dycore {
   int peer[4] = {0, 0, 0, 0};
   double *hsend[4] = {nullptr}, *hrecv[4] = {nullptr}, *msend[4] = {nullptr}, *mrecv[4] = {nullptr};
   size_t hcount[4] = {0}, mcount[4] = {0};
+  // halo exchange overlapped with interior compute: exchanges run on their own stream
+  cudaStream_t cs = nullptr, cs2 = nullptr;                // exchange stream; second compute stream for the boundary tiles
+  cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_prev = nullptr, ev_bnd = nullptr;
+  bool overlap = false, halo_inflight = false;
   // timing
   bool timing = false;
   std::vector<cudaEvent_t> ev;         // [0]=step begin, [1]=step end, then pairs per stage kernel
@@ -152,6 +157,7 @@ static StageParams base_params(const mw_dycore *h) {
   for (int t = 0; t < c.num_tracers; ++t) if (c.tracer_positive[t]) pm |= 1u << t;
   P.positive_mask = pm;
   P.use_tma = h->use_tma;
+  P.tile_mode = 0;
   // FCT donors across interior rank boundaries (never across the global periodic seam, see StageParams)
   P.mult_W = (h->dir_active[0] && c.px > 0) ? h->mrecv[0] : nullptr;
   P.mult_E = (h->dir_active[1] && c.px < c.nproc_x - 1) ? h->mrecv[1] : nullptr;
@@ -236,6 +242,9 @@ extern "C" int mw_dycore_destroy(mw_dycore *h) {
   if (h->dev_fields_alloc) for (int f = 0; f < h->N; ++f) cudaFree(h->dev_fields[f]);
   for (int d = 0; d < 4; ++d) { cudaFree(h->hsend[d]); cudaFree(h->hrecv[d]); cudaFree(h->msend[d]); cudaFree(h->mrecv[d]); }
   for (auto e : h->ev) cudaEventDestroy(e);
+  if (h->cs) cudaStreamDestroy(h->cs);
+  if (h->cs2) cudaStreamDestroy(h->cs2);
+  for (cudaEvent_t e : {h->ev_ready, h->ev_halo, h->ev_prev, h->ev_bnd}) if (e) cudaEventDestroy(e);
   delete h;
   return MW_OK;
 }
@@ -380,6 +389,7 @@ static int exchange_mult(mw_dycore *h, cudaStream_t st) {
 }
 
 static int finish_stage(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st);
+static int finish_stage_local(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st, bool mult_done);
 template <int NT, int VAR>
 static int launch_stage_v(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
   constexpr int TILE_X = Tile<NT, VAR>::X, TILE_Y = Tile<NT, VAR>::Y, MINB = Tile<NT, VAR>::MINB;
@@ -403,11 +413,13 @@ static int launch_stage_v(mw_dycore *h, const StageParams &P, int in_buf, cudaSt
   h->launches++;
   return finish_stage(h, P, NT, st);
 }
-// tracer finish (FCT-scaled divergence, RK, clip) and the halo exchange of the new state
-static int finish_stage(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st) {
+// tracer finish (FCT-scaled divergence, RK, clip); with decomposed directions the neighbours' FCT factors come first
+static int finish_stage_local(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st, bool mult_done = false) {
   if (nt > 0) {
-    int rc = exchange_mult(h, st);
-    if (rc != MW_OK) return rc;
+    if (!mult_done) {
+      int rc = exchange_mult(h, st);
+      if (rc != MW_OK) return rc;
+    }
     const long long ncell = (long long) P.nz * P.ny * P.nx;
     const unsigned g = (unsigned) ((ncell + 255) / 256);
     switch (nt) {
@@ -419,30 +431,76 @@ static int finish_stage(mw_dycore *h, const StageParams &P, int nt, cudaStream_t
     MW_CUDA_OK(cudaGetLastError());
     h->launches++;
   }
+  return MW_OK;
+}
+// ... followed by the halo exchange of the new state on the same stream (no overlap)
+static int finish_stage(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st) {
+  int rc = finish_stage_local(h, P, nt, st);
+  if (rc != MW_OK) return rc;
   return exchange_halos(h, P.qout, st);
 }
+// start the width-3 halo exchange of buffer q on the exchange stream once everything queued on `st` has finished
+static int exchange_halos_async(mw_dycore *h, double *q, cudaStream_t st) {
+  MW_CUDA_OK(cudaEventRecord(h->ev_ready, st));
+  MW_CUDA_OK(cudaStreamWaitEvent(h->cs, h->ev_ready, 0));
+  int rc = exchange_halos(h, q, h->cs);
+  if (rc != MW_OK) return rc;
+  MW_CUDA_OK(cudaEventRecord(h->ev_halo, h->cs));
+  h->halo_inflight = true;
+  return MW_OK;
+}
 template <int NT>
-static int launch_stage_ws(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
+static int launch_stage_ws(mw_dycore *h, const StageParams &P0, int in_buf, cudaStream_t st, bool last) {
   using C = WsCfg<NT, 16, 8>;
   static bool attr_set = false;
   if (!attr_set) {
     MW_CUDA_OK(cudaFuncSetAttribute(k_stage_ws<NT, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
     attr_set = true;
   }
-  dim3 grid((P.nx + 15) / 16, (P.ny + 7) / 8);
+  StageParams P = P0;
+  const int nbx = (P.nx + 15) / 16, nby = (P.ny + 7) / 8;
   if (h->timing) {
     while (h->ev.size() < (size_t) (4 + 2 * h->n_stage_timed)) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
     cudaEventRecord(h->ev[2 + 2 * h->n_stage_timed], st);
   }
-  k_stage_ws<NT, 16, 8><<<grid, C::NTHR, C::SMEM, st>>>(h->tmap[in_buf], P);
+  if (!h->overlap) {
+    k_stage_ws<NT, 16, 8><<<dim3(nbx, nby), C::NTHR, C::SMEM, st>>>(h->tmap[in_buf], P);
+    h->launches++;
+  } else {
+    // Tiles whose stencil reaches a halo filled by a neighbour rank wait for the exchange; the others ("interior")
+    // run while it is in flight.  Both sets are launched as concurrent kernels (second compute stream) so that the
+    // small boundary launch fills SMs next to the interior launch instead of adding a wave of its own.
+    P.nbx = nbx; P.nby = nby;
+    P.tbx_lo = h->dir_active[0] ? 1 : 0; P.tbx_hi = h->dir_active[0] ? std::max((P.nx - HALO) / 16, 0) : nbx;
+    P.tby_lo = h->dir_active[2] ? 1 : 0; P.tby_hi = h->dir_active[2] ? std::max((P.ny - HALO) / 8, 0) : nby;
+    int n_int = (P.tbx_hi > P.tbx_lo && P.tby_hi > P.tby_lo) ? (P.tbx_hi - P.tbx_lo) * (P.tby_hi - P.tby_lo) : 0;
+    if (n_int == 0) { P.tbx_lo = P.tbx_hi = 0; P.tby_lo = nby; P.tby_hi = nby; }   // everything is boundary ("low" rows)
+    MW_CUDA_OK(cudaEventRecord(h->ev_prev, st));
+    if (n_int > 0) {
+      P.tile_mode = 1;
+      k_stage_ws<NT, 16, 8><<<n_int, C::NTHR, C::SMEM, st>>>(h->tmap[in_buf], P);
+      h->launches++;
+    }
+    MW_CUDA_OK(cudaStreamWaitEvent(h->cs2, h->ev_prev, 0));
+    if (h->halo_inflight) { MW_CUDA_OK(cudaStreamWaitEvent(h->cs2, h->ev_halo, 0)); h->halo_inflight = false; }
+    P.tile_mode = 2;
+    k_stage_ws<NT, 16, 8><<<nbx * nby - n_int, C::NTHR, C::SMEM, h->cs2>>>(h->tmap[in_buf], P);
+    h->launches++;
+    // the boundary cells' FCT factors go to the neighbours as soon as the boundary tiles are done (also overlapped)
+    if (NT > 0) { int rc = exchange_mult(h, h->cs2); if (rc != MW_OK) return rc; }
+    MW_CUDA_OK(cudaEventRecord(h->ev_bnd, h->cs2));
+    MW_CUDA_OK(cudaStreamWaitEvent(st, h->ev_bnd, 0));
+  }
   MW_CUDA_OK(cudaGetLastError());
   if (h->timing) { cudaEventRecord(h->ev[3 + 2 * h->n_stage_timed], st); h->n_stage_timed++; }
-  h->launches++;
-  return finish_stage(h, P, NT, st);
+  if (!h->overlap) return finish_stage(h, P0, NT, st);
+  int rc = finish_stage_local(h, P0, NT, st, true);
+  if (rc != MW_OK) return rc;
+  return last ? MW_OK : exchange_halos_async(h, P0.qout, st);      // the last stage's halos are never read
 }
 template <int NT>
-static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
-  if constexpr (NT <= 3) { if (tile_variant(NT) == 2) return launch_stage_ws<NT>(h, P, in_buf, st); }
+static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st, bool last) {
+  if constexpr (NT <= 3) { if (tile_variant(NT) == 2) return launch_stage_ws<NT>(h, P, in_buf, st, last); }
   if constexpr (NT <= 1) { if (tile_variant(NT) == 1) return launch_stage_v<NT, 1>(h, P, in_buf, st); }
   return launch_stage_v<NT, 0>(h, P, in_buf, st);
 }
@@ -472,7 +530,7 @@ static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaSt
   MW_CUDA_OK(cudaGetLastError());
   h->launches++;
   {
-    int rc = exchange_halos(h, h->q[0], st);
+    int rc = h->overlap ? exchange_halos_async(h, h->q[0], st) : exchange_halos(h, h->q[0], st);
     if (rc != MW_OK) return rc;
   }
 
@@ -488,7 +546,7 @@ static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaSt
       else             { in_buf = 2; P.qout = h->q[0]; P.rk_a = 1. / 3.; P.rk_b = 2. / 3.; P.rk_cdt = (2. / 3.) * dt_dyn;   P.dt_stage = (2. / 3.) * dt_dyn; }
       P.qin = h->q[in_buf];
       P.q0 = h->q[0];
-      int rc = launch_stage<NT>(h, P, in_buf, st);
+      int rc = launch_stage<NT>(h, P, in_buf, st, ic == ncycles - 1 && s == 2);
       if (rc != MW_OK) return rc;
     }
   }
@@ -547,6 +605,19 @@ extern "C" int mw_dycore_attach_comm(mw_dycore *h, mw_comm *comm) {
   h->peer[3] = wrap(c.py + 1, c.nproc_y) * c.nproc_x + c.px;
   h->dir_active[0] = h->dir_active[1] = (c.nproc_x > 1);
   h->dir_active[2] = h->dir_active[3] = (c.nproc_y > 1) && !sim2d;
+  {
+    const char *e = getenv("MW_NO_OVERLAP");
+    h->overlap = (h->dir_active[0] || h->dir_active[2]) && tile_variant(c.num_tracers) == 2 && !(e && atoi(e) != 0);
+    if (h->overlap && !h->cs) {
+      // high priority: the few boundary CTAs and the pack / NCCL / unpack kernels are dispatched ahead of the queued
+      // interior CTAs as SMs free up, so they never form a tail of their own
+      int prio_lo = 0, prio_hi = 0;
+      MW_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      MW_CUDA_OK(cudaStreamCreateWithPriority(&h->cs, cudaStreamNonBlocking, prio_hi));
+      MW_CUDA_OK(cudaStreamCreateWithPriority(&h->cs2, cudaStreamNonBlocking, prio_hi));
+      for (cudaEvent_t *e : {&h->ev_ready, &h->ev_halo, &h->ev_prev, &h->ev_bnd}) MW_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+  }
   const size_t T = c.num_tracers;
   for (int d = 0; d < 4; ++d) {
     if (!h->dir_active[d]) continue;

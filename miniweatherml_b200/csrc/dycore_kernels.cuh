@@ -42,7 +42,28 @@ struct StageParams {
   const double *mult_W, *mult_E, *mult_S, *mult_N;
   unsigned positive_mask;    // bit tr set <=> tracer tr must stay non-negative
   int use_tma;
+  // which tiles a launch covers (halo exchange overlapped with interior compute): 0 = all (2-D grid), 1 = the interior
+  // rectangle [tbx_lo,tbx_hi) x [tby_lo,tby_hi) of tiles, 2 = every tile outside it (1-D grids); nbx = tiles per row
+  int tile_mode, tbx_lo, tbx_hi, tby_lo, tby_hi, nbx, nby;
 };
+
+__device__ __forceinline__ void tile_coords(const StageParams &P, int &bx, int &by) {
+  if (P.tile_mode == 0) { bx = blockIdx.x; by = blockIdx.y; return; }
+  int idx = blockIdx.x;
+  if (P.tile_mode == 1) {
+    const int w = P.tbx_hi - P.tbx_lo;
+    by = P.tby_lo + idx / w; bx = P.tbx_lo + idx % w;
+    return;
+  }
+  const int A = P.tby_lo * P.nbx, B = (P.nby - P.tby_hi) * P.nbx;
+  if (idx < A) { by = idx / P.nbx; bx = idx % P.nbx; return; }
+  idx -= A;
+  if (idx < B) { by = P.tby_hi + idx / P.nbx; bx = idx % P.nbx; return; }
+  idx -= B;
+  const int wm = P.tbx_lo + P.nbx - P.tbx_hi, r = idx / wm, c = idx % wm;
+  by = P.tby_lo + r;
+  bx = c < P.tbx_lo ? c : P.tbx_hi + (c - P.tbx_lo);
+}
 
 // --------------------------------------------------------------------------------------------------------
 // small helpers
@@ -172,7 +193,9 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
   unsigned *fdesc = rdesc + C::ROUNDS * C::NTHR;                                     // my face descriptors
 
   const int tid = threadIdx.x;
-  const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+  int tbx, tby;
+  tile_coords(P, tbx, tby);
+  const int i0 = tbx * TX, j0 = tby * TY;
   const int nz = P.nz;
   const bool wall = (P.bc_z == MW_BC_WALL);
   const bool use_tma = P.use_tma != 0;

@@ -89,7 +89,9 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
   uint64_t *full_bar = tma_bar + NSLOT, *empty_bar = full_bar + 2;
 
   const int tid = threadIdx.x;
-  const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+  int tbx, tby;
+  tile_coords(P, tbx, tby);
+  const int i0 = tbx * TX, j0 = tby * TY;
   const int nz = P.nz;
   const bool wall = (P.bc_z == MW_BC_WALL);
   const long long plane_cells = (long long) P.ny * P.nx;
