@@ -3,6 +3,7 @@
 // (reference: model/modules/dynamics_euler_stratified_wenofv.h:81-198).
 #include "dycore_kernels.cuh"
 #include "stage_ws.cuh"
+#include "stage_uj.cuh"
 #include "comm.cuh"
 #include <cmath>
 #include <algorithm>
@@ -90,6 +91,7 @@ static int tile_variant(int nt) {
     const char *t = getenv("MW_NO_TMA");
     if (t && atoi(t) != 0) v = 0;                           // the plain-load path exists in the phase kernel only
   }
+  if (v == 3) return nt <= 1 ? 3 : (nt <= 3 ? 2 : 0);    // uniform-jobs kernel (stage_uj.cuh) where it fits in smem
   if (v == 2) return nt <= 3 ? 2 : 0;
   return (nt <= 1) ? v : 0;
 }
@@ -113,6 +115,7 @@ struct mw_dycore {
   mw_comm *comm = nullptr;
   long long launches = 0;
   int use_tma = 1;
+  unsigned long long *prof = nullptr;  // MW_STAGE_PROF=1: wait accounting of k_stage_uj (managed memory), printed on destroy
   // staging for the *_host entry point
   double *dev_fields[NUM_STATE + MW_MAX_TRACERS] = {nullptr};
   bool dev_fields_alloc = false;
@@ -158,6 +161,7 @@ static StageParams base_params(const mw_dycore *h) {
   P.positive_mask = pm;
   P.use_tma = h->use_tma;
   P.tile_mode = 0;
+  P.prof = h->prof;
   // FCT donors across interior rank boundaries (never across the global periodic seam, see StageParams)
   P.mult_W = (h->dir_active[0] && c.px > 0) ? h->mrecv[0] : nullptr;
   P.mult_E = (h->dir_active[1] && c.px < c.nproc_x - 1) ? h->mrecv[1] : nullptr;
@@ -207,6 +211,8 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   h->qbytes = (size_t) h->N * h->vstride * sizeof(double);
   const char *e = getenv("MW_NO_TMA");
   h->use_tma = (e && atoi(e) != 0) ? 0 : 1;
+  const char *pe = getenv("MW_STAGE_PROF");
+  if (pe && atoi(pe) != 0 && cudaMallocManaged(&h->prof, 8 * sizeof(unsigned long long)) == cudaSuccess) memset(h->prof, 0, 64);
   const int T = cfg->num_tracers > 0 ? cfg->num_tracers : 1;
   const size_t nzl = cfg->nz, nyl = cfg->ny, nxl = cfg->nx;
   cudaError_t ce = cudaSuccess;
@@ -237,6 +243,15 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
 
 extern "C" int mw_dycore_destroy(mw_dycore *h) {
   if (!h) return MW_OK;
+  if (h->prof) {
+    cudaDeviceSynchronize();
+    const unsigned long long *p = h->prof;
+    const double n = p[6] ? (double) p[6] : 1.0;
+    fprintf(stderr, "[mw stage prof] CTAs %llu  R: total %.0f cyc, wait-for-U %.1f%%, wait-for-TMA %.1f%%   U: total %.0f cyc, wait-for-R %.1f%%, "
+            "named barriers %.1f%%\n", p[6], p[0] / n, 100.0 * p[1] / (p[0] + 1.0), 100.0 * p[2] / (p[0] + 1.0), p[3] / n,
+            100.0 * p[4] / (p[3] + 1.0), 100.0 * p[5] / (p[3] + 1.0));
+    cudaFree(h->prof);
+  }
   for (int b = 0; b < 3; ++b) cudaFree(h->q[b]);
   cudaFree(h->flux_x); cudaFree(h->flux_y); cudaFree(h->flux_z); cudaFree(h->mult); cudaFree(h->bg);
   if (h->dev_fields_alloc) for (int f = 0; f < h->N; ++f) cudaFree(h->dev_fields[f]);
@@ -449,12 +464,24 @@ static int exchange_halos_async(mw_dycore *h, double *q, cudaStream_t st) {
   h->halo_inflight = true;
   return MW_OK;
 }
-template <int NT>
-static int launch_stage_ws(mw_dycore *h, const StageParams &P0, int in_buf, cudaStream_t st, bool last) {
+// KIND 2: warp-specialised kernel with register z windows (stage_ws.cuh); KIND 3: uniform-jobs kernel (stage_uj.cuh)
+template <int NT, int KIND> struct WsKernel;
+template <int NT> struct WsKernel<NT, 2> {
   using C = WsCfg<NT, 16, 8>;
+  static void launch(dim3 g, cudaStream_t st, const CUtensorMap &m, const StageParams &P) { k_stage_ws<NT, 16, 8><<<g, C::NTHR, C::SMEM, st>>>(m, P); }
+  static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_ws<NT, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
+};
+template <int NT> struct WsKernel<NT, 3> {
+  using C = UjCfg<NT, 16, 8>;
+  static void launch(dim3 g, cudaStream_t st, const CUtensorMap &m, const StageParams &P) { k_stage_uj<NT, 16, 8><<<g, C::NTHR, C::SMEM, st>>>(m, P); }
+  static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_uj<NT, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
+};
+template <int NT, int KIND = 2>
+static int launch_stage_ws(mw_dycore *h, const StageParams &P0, int in_buf, cudaStream_t st, bool last) {
+  using K = WsKernel<NT, KIND>;
   static bool attr_set = false;
   if (!attr_set) {
-    MW_CUDA_OK(cudaFuncSetAttribute(k_stage_ws<NT, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
+    MW_CUDA_OK(K::attr());
     attr_set = true;
   }
   StageParams P = P0;
@@ -464,7 +491,7 @@ static int launch_stage_ws(mw_dycore *h, const StageParams &P0, int in_buf, cuda
     cudaEventRecord(h->ev[2 + 2 * h->n_stage_timed], st);
   }
   if (!h->overlap) {
-    k_stage_ws<NT, 16, 8><<<dim3(nbx, nby), C::NTHR, C::SMEM, st>>>(h->tmap[in_buf], P);
+    K::launch(dim3(nbx, nby), st, h->tmap[in_buf], P);
     h->launches++;
   } else {
     // Tiles whose stencil reaches a halo filled by a neighbour rank wait for the exchange; the others ("interior")
@@ -478,13 +505,13 @@ static int launch_stage_ws(mw_dycore *h, const StageParams &P0, int in_buf, cuda
     MW_CUDA_OK(cudaEventRecord(h->ev_prev, st));
     if (n_int > 0) {
       P.tile_mode = 1;
-      k_stage_ws<NT, 16, 8><<<n_int, C::NTHR, C::SMEM, st>>>(h->tmap[in_buf], P);
+      K::launch(dim3(n_int), st, h->tmap[in_buf], P);
       h->launches++;
     }
     MW_CUDA_OK(cudaStreamWaitEvent(h->cs2, h->ev_prev, 0));
     if (h->halo_inflight) { MW_CUDA_OK(cudaStreamWaitEvent(h->cs2, h->ev_halo, 0)); h->halo_inflight = false; }
     P.tile_mode = 2;
-    k_stage_ws<NT, 16, 8><<<nbx * nby - n_int, C::NTHR, C::SMEM, h->cs2>>>(h->tmap[in_buf], P);
+    K::launch(dim3(nbx * nby - n_int), h->cs2, h->tmap[in_buf], P);
     h->launches++;
     // the boundary cells' FCT factors go to the neighbours as soon as the boundary tiles are done (also overlapped)
     if (NT > 0) { int rc = exchange_mult(h, h->cs2); if (rc != MW_OK) return rc; }
@@ -500,7 +527,8 @@ static int launch_stage_ws(mw_dycore *h, const StageParams &P0, int in_buf, cuda
 }
 template <int NT>
 static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st, bool last) {
-  if constexpr (NT <= 3) { if (tile_variant(NT) == 2) return launch_stage_ws<NT>(h, P, in_buf, st, last); }
+  if constexpr (NT <= 1) { if (tile_variant(NT) == 3) return launch_stage_ws<NT, 3>(h, P, in_buf, st, last); }
+  if constexpr (NT <= 3) { if (tile_variant(NT) == 2) return launch_stage_ws<NT, 2>(h, P, in_buf, st, last); }
   if constexpr (NT <= 1) { if (tile_variant(NT) == 1) return launch_stage_v<NT, 1>(h, P, in_buf, st); }
   return launch_stage_v<NT, 0>(h, P, in_buf, st);
 }
@@ -607,7 +635,7 @@ extern "C" int mw_dycore_attach_comm(mw_dycore *h, mw_comm *comm) {
   h->dir_active[2] = h->dir_active[3] = (c.nproc_y > 1) && !sim2d;
   {
     const char *e = getenv("MW_NO_OVERLAP");
-    h->overlap = (h->dir_active[0] || h->dir_active[2]) && tile_variant(c.num_tracers) == 2 && !(e && atoi(e) != 0);
+    h->overlap = (h->dir_active[0] || h->dir_active[2]) && tile_variant(c.num_tracers) >= 2 && !(e && atoi(e) != 0);
     if (h->overlap && !h->cs) {
       // high priority: the few boundary CTAs and the pack / NCCL / unpack kernels are dispatched ahead of the queued
       // interior CTAs as SMs free up, so they never form a tail of their own

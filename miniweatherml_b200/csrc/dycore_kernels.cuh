@@ -45,6 +45,10 @@ struct StageParams {
   // which tiles a launch covers (halo exchange overlapped with interior compute): 0 = all (2-D grid), 1 = the interior
   // rectangle [tbx_lo,tbx_hi) x [tby_lo,tby_hi) of tiles, 2 = every tile outside it (1-D grids); nbx = tiles per row
   int tile_mode, tbx_lo, tbx_hi, tby_lo, tby_hi, nbx, nby;
+  // optional in-kernel wait accounting (MW_STAGE_PROF=1, k_stage_uj only): cycles summed over one probe thread per role
+  // and CTA: [0] R total, [1] R waiting for U (empty), [2] R waiting for TMA, [3] U total, [4] U waiting for R (full),
+  // [5] U in its named barriers, [6] CTAs
+  unsigned long long *prof;
 };
 
 __device__ __forceinline__ void tile_coords(const StageParams &P, int &bx, int &by) {
