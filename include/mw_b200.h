@@ -95,6 +95,7 @@ int  mw_dycore_set_background(mw_dycore *h, const double *hy_dens_cells, const d
 /* read them back (host pointers), e.g. to register "hy_dens_cells" in the DataManager (DYC:1663-1668) */
 int  mw_dycore_get_background(mw_dycore *h, double *hy_dens_cells, double *hy_dens_theta_cells,
                               double *hy_dens_edges, double *hy_dens_theta_edges);
+/* installs (non-NULL) or removes (NULL) the immersed_proportion mask; use_immersed_boundaries follows it */
 int  mw_dycore_set_immersed(mw_dycore *h, const double *immersed_proportion /* device [nz][ny][nx] or NULL */);
 double mw_dycore_compute_time_step(const mw_dycore *h);
 /* fields: host array of 5+T DEVICE pointers in coupler order (density_dry,uvel,vvel,wvel,temp,tracers...) */
@@ -104,6 +105,20 @@ int  mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields, double d
 /* supercell initial condition (hydrostatic GLL-quadrature column + cell averages) straight into coupler fields
  * and into the handle's background profiles */
 int  mw_dycore_init_supercell(mw_dycore *h, double *const *fields, void *stream);
+/* the other init_data test cases of Dynamics_Euler_Stratified_WenoFV::init (DYC:1338-1653), written into the coupler
+ * fields, the handle's background profiles and (building / city) the immersed_proportion mask:
+ *   thermal  : rising moist bubble over a constant-theta hydrostatic column, 3-point Gauss-Legendre (DYC:1338-1419)
+ *   building : uniform u = 20 m/s flow, one immersed block (DYC:1544-1651); honours enable_gravity
+ *   city     : uniform u = 20 m/s flow, a grid of immersed buildings whose heights the caller draws exactly like the
+ *              reference (std::mt19937{17}, normal(60,10), row-major [nby][nbx]; DYC:1431-1451, 1506-1512)
+ * `immersed` is a DEVICE [nz][ny][nx] array owned by the caller (the "immersed_proportion" DataManager entry); it is
+ * filled and installed as the handle's mask (use_immersed_boundaries = true, DYC:1424,1548). */
+int  mw_dycore_init_thermal(mw_dycore *h, double *const *fields, void *stream);
+int  mw_dycore_init_building(mw_dycore *h, double *const *fields, double *immersed, void *stream);
+int  mw_city_layout(double xlen, double ylen, int nx_glob, int *cells_per_building, int *nbuildings_y,
+                    int *nbuildings_x);                              /* DYC:1430-1437 */
+int  mw_dycore_init_city(mw_dycore *h, double *const *fields, double *immersed, const double *building_heights_host,
+                         int nbuildings_y, int nbuildings_x, void *stream);
 /* attach a communicator: halos of decomposed directions then go through NCCL send/recv instead of a local wrap */
 int  mw_dycore_attach_comm(mw_dycore *h, mw_comm *comm);
 /* diagnostics: number of kernels this handle launched since creation */
@@ -148,6 +163,22 @@ int  mw_nudge_to_column(double *const *f5, int nz, int ny, int nx, long long nx_
                         const double *column, mw_comm *comm, void *stream);
 int  mw_perturb_temperature(double *temp, int nz, int ny, int nx, int i_beg, int j_beg, double dx, double dy,
                             double dz, double xlen, double ylen, void *stream);
+
+/* ---- experiments/simple_city custom modules ------------------------------------------------------------------ */
+/* Horizontal_Sponge::init (horizontal_sponge.h:18-92): column[nfields][nz] (device) <- cell (k,0,0) of each field on
+ * rank 0, broadcast to every rank when comm != NULL */
+int  mw_extract_column(int nfields, const double *const *fields, int nz, int ny, int nx, double *column,
+                       mw_comm *comm, void *stream);
+/* Horizontal_Sponge::apply (horizontal_sponge.h:103-193): relax the `sponge_cells` outermost cells of each enabled
+ * side towards column[f][k] with weight (cos(pi*d/(sponge_cells-1))+1)/2 * dt/time_scale, sides applied in the
+ * reference's order x1, x2, y1, y2; a side is active only on the ranks that own it (px == 0, px == nproc_x-1, ...) */
+int  mw_horizontal_sponge_apply(int nfields, double *const *fields, const double *column, int nz, int ny, int nx,
+                                int sponge_cells, double time_scale, double dt, int x1, int x2, int y1, int y2,
+                                int px, int nproc_x, int py, int nproc_y, void *stream);
+/* Time_Averager::accumulate (time_averager.h:34-66): inertia = etime/(etime+dt); avg <- inertia*avg + (1-inertia)*val
+ * for nfields fields of n cells (the caller advances etime) */
+int  mw_time_average_accumulate(int nfields, double *const *avg, const double *const *val, long long n, double etime,
+                                double dt, void *stream);
 
 /* ---- communicator (NCCL over NVLink), one process per GPU -------------------------------------------------- */
 int  mw_comm_unique_id(void *id_bytes_128);                       /* rank 0 creates, caller broadcasts            */

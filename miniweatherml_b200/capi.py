@@ -73,6 +73,13 @@ def lib():
         ("mw_column_average", [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_longlong, vp, vp, vp]),
         ("mw_nudge_to_column", [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_double, vp, vp, vp]),
         ("mw_perturb_temperature", [vp] + [C.c_int] * 5 + [C.c_double] * 5 + [vp]),
+        ("mw_dycore_init_thermal", [vp, C.POINTER(vp), vp]),
+        ("mw_dycore_init_building", [vp, C.POINTER(vp), vp, vp]),
+        ("mw_city_layout", [C.c_double, C.c_double, C.c_int, ip, ip, ip]),
+        ("mw_dycore_init_city", [vp, C.POINTER(vp), vp, dp, C.c_int, C.c_int, vp]),
+        ("mw_extract_column", [C.c_int, C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+        ("mw_horizontal_sponge_apply", [C.c_int, C.POINTER(vp), vp] + [C.c_int] * 4 + [C.c_double] * 2 + [C.c_int] * 8 + [vp]),
+        ("mw_time_average_accumulate", [C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_longlong, C.c_double, C.c_double, vp]),
         ("mw_comm_unique_id", [vp]),
         ("mw_comm_create", [vp, C.c_int, C.c_int, C.POINTER(vp)]),
         ("mw_comm_destroy", [vp]),
@@ -183,6 +190,23 @@ class Dycore:
         arr = (C.c_void_p * self.N)(*[t.data_ptr() for t in fields])
         _check(lib().mw_dycore_init_supercell(self.h, arr, _stream()))
 
+    def init_thermal(self, fields):
+        arr = (C.c_void_p * self.N)(*[t.data_ptr() for t in fields])
+        _check(lib().mw_dycore_init_thermal(self.h, arr, _stream()))
+
+    def init_building(self, fields, immersed):
+        """fields + immersed_proportion [nz,ny,nx] filled; the mask is installed in the handle (DYC:1544-1651)"""
+        arr = (C.c_void_p * self.N)(*[t.data_ptr() for t in fields])
+        self._immersed = immersed
+        _check(lib().mw_dycore_init_building(self.h, arr, _ptr(immersed), _stream()))
+
+    def init_city(self, fields, immersed, heights):
+        """heights: numpy [nbuildings_y, nbuildings_x] drawn like DYC:1442-1449 (see city_layout)"""
+        arr = (C.c_void_p * self.N)(*[t.data_ptr() for t in fields])
+        h = np.ascontiguousarray(heights, dtype=np.float64)
+        self._immersed = immersed
+        _check(lib().mw_dycore_init_city(self.h, arr, _ptr(immersed), _dp(h), h.shape[0], h.shape[1], _stream()))
+
     def attach_comm(self, comm):
         _check(lib().mw_dycore_attach_comm(self.h, comm))
 
@@ -273,3 +297,32 @@ def nudge_to_column(f5, column, dt, nxy_glob=None, comm=None):
 def perturb_temperature(temp, i_beg, j_beg, dx, dy, dz, xlen, ylen):
     nz, ny, nx = temp.shape
     _check(lib().mw_perturb_temperature(_ptr(temp), nz, ny, nx, i_beg, j_beg, dx, dy, dz, xlen, ylen, _stream()))
+
+
+def city_layout(xlen, ylen, nx_glob):
+    """(cells_per_building, nbuildings_y, nbuildings_x) of init_data = city (DYC:1430-1437)"""
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().mw_city_layout(xlen, ylen, nx_glob, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
+def extract_column(fields, comm=None):
+    """Horizontal_Sponge::init: column[f][k] = field_f(k,0,0) of rank 0, broadcast (horizontal_sponge.h:18-92)"""
+    import torch
+    nz, ny, nx = fields[0].shape
+    col = torch.empty((len(fields), nz), dtype=torch.float64, device=fields[0].device)
+    _check(lib().mw_extract_column(len(fields), _ptr_array(fields), nz, ny, nx, _ptr(col), comm, _stream()))
+    return col
+
+
+def horizontal_sponge_apply(fields, column, dt, sponge_cells=10, time_scale=1.0, x1=True, x2=True, y1=True, y2=True,
+                            px=0, nproc_x=1, py=0, nproc_y=1):
+    nz, ny, nx = fields[0].shape
+    _check(lib().mw_horizontal_sponge_apply(len(fields), _ptr_array(fields), _ptr(column), nz, ny, nx, sponge_cells,
+                                            time_scale, dt, int(x1), int(x2), int(y1), int(y2), px, nproc_x, py, nproc_y,
+                                            _stream()))
+
+
+def time_average_accumulate(avg, val, etime, dt):
+    _check(lib().mw_time_average_accumulate(len(avg), _ptr_array(avg), _ptr_array(val), avg[0].numel(), etime, dt,
+                                            _stream()))

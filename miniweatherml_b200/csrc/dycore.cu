@@ -297,6 +297,7 @@ extern "C" int mw_dycore_get_background(mw_dycore *h, double *hyc, double *hytc,
 extern "C" int mw_dycore_set_immersed(mw_dycore *h, const double *immersed) {
   MW_REQUIRE(h, "mw_dycore_set_immersed: null handle");
   h->immersed = immersed;
+  h->cfg.use_immersed_boundaries = immersed ? 1 : 0;      // the "use_immersed_boundaries" option follows the mask (DYC:1424,1548)
   return MW_OK;
 }
 

@@ -4,6 +4,7 @@
 // BASELINE.json calls this class "Dynamics_Euler_Stateless"; an alias is provided below.
 #pragma once
 #include "coupler.h"
+#include <random>
 
 namespace modules {
 class Dynamics_Euler_Stratified_WenoFV {
@@ -110,15 +111,12 @@ class Dynamics_Euler_Stratified_WenoFV {
     cfg.enable_gravity = coupler.get_option<bool>("enable_gravity", true) ? 1 : 0;
     cfg.use_immersed_boundaries = 0;
 
-    if (init_data == "supercell") {                                 // DYC:1330-1337
-      coupler.add_option<int>("bc_x", BC_PERIODIC);
-      coupler.add_option<int>("bc_y", BC_PERIODIC);
-      coupler.add_option<int>("bc_z", BC_WALL);
-      coupler.add_option<real>("latitude", 0);
-    } else {
-      endrun("ERROR: init_data [" + init_data + "]: the B200 path implements the supercell test case "
-             "(thermal / city / building initialisers are SURVEY 8(f) rows, not built yet)");
-    }
+    bool const known = init_data == "supercell" || init_data == "thermal" || init_data == "city" || init_data == "building";
+    if (!known) endrun("ERROR: Invalid init_data in yaml input file");                        // DYC:1318
+    coupler.add_option<int>("bc_x", BC_PERIODIC);                     // DYC:1332-1335, 1340-1343, 1423-1425, 1546-1548
+    coupler.add_option<int>("bc_y", BC_PERIODIC);
+    coupler.add_option<int>("bc_z", BC_WALL);
+    if (init_data == "supercell" || init_data == "thermal") coupler.add_option<real>("latitude", 0);
     cfg.bc_x = coupler.get_option<int>("bc_x"); cfg.bc_y = coupler.get_option<int>("bc_y"); cfg.bc_z = coupler.get_option<int>("bc_z");
     cfg.latitude = coupler.get_option<real>("latitude");
     mw::check(mw_dycore_create(&cfg, &handle), "mw_dycore_create");
@@ -127,8 +125,28 @@ class Dynamics_Euler_Stratified_WenoFV {
     field_ptrs.clear();
     for (auto nm : {"density_dry", "uvel", "vvel", "wvel", "temp"}) field_ptrs.push_back(dm.get<real, 4>(nm).data());
     for (auto &nm : tracer_names) field_ptrs.push_back(dm.get<real, 4>(nm).data());
-    // init_supercell + convert_dynamics_to_coupler (DYC:1687-1887, 1656)
-    mw::check(mw_dycore_init_supercell(handle, field_ptrs.data(), nullptr), "mw_dycore_init_supercell");
+    // the test case's state + convert_dynamics_to_coupler (DYC:1656), and for building / city the immersed mask
+    if (init_data == "supercell") {                                 // DYC:1687-1887
+      mw::check(mw_dycore_init_supercell(handle, field_ptrs.data(), nullptr), "mw_dycore_init_supercell");
+    } else if (init_data == "thermal") {                            // DYC:1338-1419
+      mw::check(mw_dycore_init_thermal(handle, field_ptrs.data(), nullptr), "mw_dycore_init_thermal");
+    } else if (init_data == "building") {                           // DYC:1544-1651
+      coupler.set_option<bool>("use_immersed_boundaries", true);
+      mw::check(mw_dycore_init_building(handle, field_ptrs.data(), dm.get<real, 4>("immersed_proportion").data(), nullptr),
+                "mw_dycore_init_building");
+    } else {                                                        // city, DYC:1421-1542
+      coupler.set_option<bool>("use_immersed_boundaries", true);
+      int cells_per_building = 0, nbuildings_y = 0, nbuildings_x = 0;
+      mw::check(mw_city_layout(coupler.get_xlen(), coupler.get_ylen(), (int) coupler.get_nx_glob(), &cells_per_building,
+                               &nbuildings_y, &nbuildings_x), "mw_city_layout");
+      // DYC:1439-1451: the main rank draws and broadcasts; the sequence is deterministic, so every rank draws it
+      std::vector<double> building_heights((size_t) std::max(nbuildings_y, 0) * std::max(nbuildings_x, 0));
+      std::mt19937 gen{17};
+      std::normal_distribution<> d{60, 10};
+      for (auto &hgt : building_heights) hgt = d(gen);
+      mw::check(mw_dycore_init_city(handle, field_ptrs.data(), dm.get<real, 4>("immersed_proportion").data(),
+                                    building_heights.data(), nbuildings_y, nbuildings_x, nullptr), "mw_dycore_init_city");
+    }
 
     // DYC:1663-1668: background profiles visible to other modules
     dm.register_and_allocate<real>("hy_dens_cells", "hydrostatic density cell averages", {nz, nens});

@@ -10,6 +10,8 @@
 //   run      key=value ...   full model run; see usage() below
 //   weno     n in.bin out.bin           n x 5 stencils -> n x 2 edge values through WenoLimiter<5> + DYC:556-571
 //   kessler  nz ncol dt in.bin out.bin  modules::Microphysics_Kessler::kessler on (theta,qv,qc,qr,rho,pk)[nz][ncol]
+//   heights  n out.bin                  the first n draws of std::mt19937{17} + std::normal_distribution<>{60,10}, the
+//                                       generator/distribution DYC:1442-1449 uses for the city's building heights
 //   mlp      B w.bin in.bin out.bin     ponni Matvec/Bias/Relu(0.1)/Matvec/Bias forward on fp32 [5][B] -> [4][B]
 #include "coupler.h"
 #include "dynamics_euler_stratified_wenofv.h"
@@ -17,10 +19,12 @@
 #include "sponge_layer.h"
 #include "perturb_temperature.h"
 #include "column_nudging.h"
+#include "horizontal_sponge.h"   // experiments/simple_city/custom_modules (via -I)
 #include "ponni.h"
 #include <chrono>
 #include <cstdio>
 #include <map>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -77,7 +81,9 @@ static void usage() {
     "ref_driver run nx= ny= nz= xlen= ylen= zlen= [nens=1] [init_data=supercell] [tracers=kessler|vapor]\n"
     "               [steps=10] [dt=0 (0 => dycore.compute_time_step)] [dycore=1] [micro=0] [sponge=0] [nudge=0]\n"
     "               [perturb=1] [in=state.bin] [out=state.bin] [out0=initial_state.bin] [bg=background.bin]\n"
-    "               [precl=precl.bin] [time=0|1 print seconds per step]\n");
+    "               [precl=precl.bin] [time=0|1 print seconds per step]\n"
+    "               [enable_gravity=1] [hsponge=0 (simple_city: Horizontal_Sponge init(10,1) + apply(x1,x2) before the dycore)]\n"
+    "               [sponge_ts=60] [imm=immersed_proportion.bin] [init_data=supercell|thermal|building|city]\n");
 }
 
 static int mode_run(std::map<std::string,std::string> &kv) {
@@ -90,12 +96,15 @@ static int mode_run(std::map<std::string,std::string> &kv) {
   double dt_in = getd("dt",0.);
   bool   do_dycore = geti("dycore",1), do_micro = geti("micro",0), do_sponge = geti("sponge",0);
   bool   do_nudge = geti("nudge",0), do_perturb = geti("perturb",1), do_time = geti("time",0);
+  bool   do_hsponge = geti("hsponge",0);
+  double sponge_ts = getd("sponge_ts",60.);
   std::string tracers = gets("tracers","kessler");
 
   core::Coupler coupler;
   coupler.set_option<std::string>( "out_prefix" , "oracle" );
   coupler.set_option<std::string>( "init_data"  , gets("init_data","supercell") );
   coupler.set_option<real       >( "out_freq"   , -1. );
+  if (kv.count("enable_gravity")) coupler.set_option<bool>( "enable_gravity" , geti("enable_gravity",1) != 0 );
   coupler.distribute_mpi_and_allocate_coupled_state(nz, ny, nx, nens);
   coupler.set_grid( xlen , ylen , zlen );
   coupler.set_option<std::string>( "standalone_input_file" , "none" );
@@ -103,6 +112,7 @@ static int mode_run(std::map<std::string,std::string> &kv) {
   modules::ColumnNudger                     column_nudger;
   modules::Microphysics_Kessler             micro;
   modules::Dynamics_Euler_Stratified_WenoFV dycore;
+  custom_modules::Horizontal_Sponge         horiz_sponge;
 
   if (tracers == "kessler") {
     micro.init( coupler );
@@ -112,11 +122,16 @@ static int mode_run(std::map<std::string,std::string> &kv) {
     if (do_micro) { fprintf(stderr,"micro=1 needs tracers=kessler\n"); return 2; }
   }
   dycore.init( coupler );
+  if (do_hsponge) horiz_sponge.init( coupler , 10 , 1. );      // experiments/simple_city/driver.cpp:60
   column_nudger.set_column( coupler );
   if (do_perturb) modules::perturb_temperature( coupler );
 
   if (kv.count("in"))   load_state(coupler, kv["in"]);
   if (kv.count("out0")) dump_state(coupler, kv["out0"]);
+  if (kv.count("imm")) {
+    auto h = coupler.get_data_manager_readonly().get_collapsed<real const>("immersed_proportion").createHostCopy();
+    write_bin(kv["imm"],h.data(),h.size());
+  }
   if (kv.count("bg")) {
     // hy_dens_cells[nz], hy_dens_theta_cells[nz], hy_dens_edges[nz+1], hy_dens_theta_edges[nz+1]  (iens = 0)
     std::vector<double> bg;
@@ -131,9 +146,10 @@ static int mode_run(std::map<std::string,std::string> &kv) {
   auto t0 = std::chrono::steady_clock::now();
   for (int s=0; s < steps; s++) {
     if (dt_in <= 0.) dtphys = dycore.compute_time_step(coupler);
+    if (do_hsponge) horiz_sponge.apply          ( coupler , dtphys , true , true , false , false );  // simple_city/driver.cpp:72
     if (do_dycore) dycore.time_step             ( coupler , dtphys );
     if (do_micro ) micro .time_step             ( coupler , dtphys );
-    if (do_sponge) modules::sponge_layer        ( coupler , dtphys );
+    if (do_sponge) modules::sponge_layer        ( coupler , dtphys , sponge_ts );
     if (do_nudge ) column_nudger.nudge_to_column( coupler , dtphys );
   }
   yakl::fence();
@@ -200,6 +216,15 @@ static int mode_kessler(int nz, int ncol, double dt, std::string in, std::string
   return 0;
 }
 
+static int mode_heights(int n, std::string out) {
+  std::mt19937 gen{17};
+  std::normal_distribution<> d{60, 10};
+  std::vector<double> h(n);
+  for (int i=0; i < n; i++) h[i] = d(gen);
+  write_bin(out,h.data(),h.size());
+  return 0;
+}
+
 static int mode_mlp(int B, std::string wfn, std::string in, std::string out) {
   // weights file (doubles holding fp32-representable values): W1[5][10], b1[10], W2[10][4], b2[4]
   auto w = read_bin(wfn);
@@ -247,6 +272,7 @@ int main(int argc, char** argv) {
         rc = mode_run(kv);
       } else if (mode == "weno"    && argc == 5) { rc = mode_weno(atoi(argv[2]),argv[3],argv[4]);
       } else if (mode == "kessler" && argc == 7) { rc = mode_kessler(atoi(argv[2]),atoi(argv[3]),atof(argv[4]),argv[5],argv[6]);
+      } else if (mode == "heights" && argc == 4) { rc = mode_heights(atoi(argv[2]),argv[3]);
       } else if (mode == "mlp"     && argc == 6) { rc = mode_mlp(atoi(argv[2]),argv[3],argv[4],argv[5]);
       } else { usage(); rc = 2; }
     }

@@ -82,6 +82,11 @@ def lib():
         _lib.mwo_column_average.argtypes = [C.c_int] * 3 + [pp, dp]
         _lib.mwo_nudge.argtypes = [C.c_int] * 3 + [C.c_double, dp, pp]
         _lib.mwo_perturb_thermal.argtypes = [C.c_int] * 5 + [C.c_double] * 5 + [dp]
+        _lib.mwo_init_thermal.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_double, C.c_double, dp, dp]
+        _lib.mwo_init_uniform_flow.argtypes = [C.POINTER(Params)] + [C.c_int] * 5 + [C.c_double] * 2 + [dp, C.c_int, C.c_int,
+                                                                                                       dp, dp, dp]
+        _lib.mwo_horizontal_sponge.argtypes = [C.c_int] * 5 + [C.c_double] * 2 + [C.c_int] * 4 + [dp, dp]
+        _lib.mwo_time_average.argtypes = [C.c_size_t, C.c_double, C.c_double, dp, dp]
     return _lib
 
 
@@ -174,6 +179,41 @@ def nudge(f5, column, dt):
 def perturb_thermal(temp, i_beg, j_beg, dx, dy, dz, xlen, ylen):
     nz, ny, nx = temp.shape
     lib().mwo_perturb_thermal(nz, ny, nx, i_beg, j_beg, dx, dy, dz, xlen, ylen, _dp(temp))
+
+
+def init_thermal(p, xlen, ylen, i_beg=0, j_beg=0):
+    """-> (fields [5+T][nz][ny][nx], bg) of init_data = thermal"""
+    fields = np.zeros((5 + p.num_tracers, p.nz, p.ny, p.nx))
+    bg = np.zeros(4 * p.nz + 2)
+    lib().mwo_init_thermal(C.byref(p), i_beg, j_beg, xlen, ylen, _dp(bg), _dp(fields))
+    return fields, bg
+
+
+def city_layout(xlen, ylen, nx_glob):
+    """(cells_per_building, nbuildings_y, nbuildings_x), DYC:1430-1437"""
+    cpb = int(np.round(30 / (xlen / nx_glob)))
+    return cpb, ((int(ylen) // 30 - 40) // 9) * 9, ((int(xlen) // 30 - 40) // 3) * 3
+
+
+def init_uniform_flow(p, xlen, ylen, city=False, heights=None, i_beg=0, j_beg=0, nx_glob=None, ny_glob=None):
+    """-> (fields, bg, immersed) of init_data = building (city=False) or city (heights [nby][nbx] required)"""
+    fields = np.zeros((5 + p.num_tracers, p.nz, p.ny, p.nx))
+    bg = np.zeros(4 * p.nz + 2)
+    imm = np.zeros((p.nz, p.ny, p.nx))
+    h = np.zeros((1, 1)) if heights is None else np.ascontiguousarray(heights, dtype=np.float64)
+    lib().mwo_init_uniform_flow(C.byref(p), 1 if city else 0, i_beg, j_beg, nx_glob or p.nx, ny_glob or p.ny, xlen, ylen,
+                                _dp(h), h.shape[0], h.shape[1], _dp(bg), _dp(fields), _dp(imm))
+    return fields, bg, imm
+
+
+def horizontal_sponge(fields, col, dt, sponge_cells=10, time_scale=1.0, sides=(True, True, False, False)):
+    nf, nz, ny, nx = fields.shape
+    lib().mwo_horizontal_sponge(nf, nz, ny, nx, sponge_cells, time_scale, dt, *[int(b) for b in sides],
+                                _dp(np.ascontiguousarray(col)), _dp(fields))
+
+
+def time_average(avg, val, etime, dt):
+    lib().mwo_time_average(avg.size, etime, dt, _dp(val), _dp(avg))
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -28,8 +28,47 @@ def run_states(tmp, nx, ny, nz, xlen, ylen, zlen, tracers, steps, **mods):
     return s0, s1, bg, meta
 
 
+def config4_and_thermal(tmp):
+    """init_data = thermal / building / city (DYC:1338-1653) and the simple_city step loop
+    (Horizontal_Sponge.apply(x1,x2) -> dycore -> sponge_layer(time_scale 1), experiments/simple_city/driver.cpp:72-74)."""
+    def run(g, steps, **mods):
+        r = O.ref_run(tmp, steps=steps, tracers="vapor", perturb=0, out0=tmp + "/s0.bin", out=tmp + "/s1.bin",
+                      bg=tmp + "/bg.bin", imm=tmp + "/imm.bin", **g, **mods)
+        shp = (6, g["nz"], g["ny"], g["nx"])
+        return (np.fromfile(tmp + "/s0.bin").reshape(shp), np.fromfile(tmp + "/s1.bin").reshape(shp),
+                np.fromfile(tmp + "/bg.bin"), np.fromfile(tmp + "/imm.bin").reshape(shp[1:]), r[-1])
+    # rising moist thermal: the bubble (radius 2 km, centred at z = 2 km) resolved by a few cells
+    g = dict(nx=20, ny=16, nz=20, xlen=8000., ylen=6400., zlen=8000.)
+    s0, s1, bg, imm, meta = run(g, 5, init_data="thermal")
+    np.savez_compressed(HERE + "/thermal_dycore5.npz", s0=s0, s1=s1, bg=bg, dt=meta["dt"], steps=5, **g)
+    g = dict(nx=24, ny=1, nz=16, xlen=9600., ylen=9600., zlen=6400.)
+    s0, s1, bg, imm, meta = run(g, 5, init_data="thermal")
+    np.savez_compressed(HERE + "/thermal2d_dycore5.npz", s0=s0, s1=s1, bg=bg, dt=meta["dt"], steps=5, **g)
+    # building: the shipped input_building.yaml physics (no gravity) on a smaller grid, full simple_city loop
+    g = dict(nx=40, ny=30, nz=12, xlen=800., ylen=600., zlen=240.)
+    s0, s1, bg, imm, meta = run(g, 6, init_data="building", enable_gravity=0, hsponge=1, sponge=1, sponge_ts=1)
+    assert imm.sum() > 0
+    np.savez_compressed(HERE + "/building_city_loop6.npz", s0=s0, s1=s1, bg=bg, imm=imm, dt=meta["dt"], steps=6,
+                        enable_gravity=0, **g)
+    s0, s1d, bg, imm, meta = run(g, 6, init_data="building", enable_gravity=0)
+    np.savez_compressed(HERE + "/building_dycore6.npz", s0=s0, s1=s1d, bg=bg, imm=imm, dt=meta["dt"], steps=6,
+                        enable_gravity=0, **g)
+    # city: dx = 30 m (1 cell per building), 3 x 9 buildings, gravity on; heights = the reference's own RNG draws
+    g = dict(nx=50, ny=50, nz=12, xlen=1500., ylen=1500., zlen=120.)
+    cpb, nby, nbx = O.city_layout(g["xlen"], g["ylen"], g["nx"])
+    subprocess.check_call([O.REF_DRIVER, "heights", str(nby * nbx), tmp + "/h.bin"], stdout=subprocess.DEVNULL)
+    heights = np.fromfile(tmp + "/h.bin").reshape(nby, nbx)
+    s0, s1, bg, imm, meta = run(g, 4, init_data="city", enable_gravity=1, hsponge=1, sponge=1, sponge_ts=1)
+    assert imm.sum() > 0 and cpb == 1
+    np.savez_compressed(HERE + "/city_loop4.npz", s0=s0, s1=s1, bg=bg, imm=imm, heights=heights, dt=meta["dt"], steps=4,
+                        enable_gravity=1, **g)
+
+
 def main():
     tmp = tempfile.mkdtemp()
+    if "--config4" in sys.argv:
+        config4_and_thermal(tmp)
+        return
     # --- config 1: shipped supercell_example grid (100 x 1 x 40, 2-D), Kessler tracers -----------------------
     g = dict(nx=100, ny=1, nz=40, xlen=1e5, ylen=1e5, zlen=2e4)
     s0, s1, bg, meta = run_states(tmp, tracers="kessler", steps=10, **g)
@@ -101,6 +140,7 @@ def main():
                           stdout=subprocess.DEVNULL)
     y = np.fromfile(tmp + "/y.bin").reshape(4, 256).astype(np.float32)
     np.savez_compressed(HERE + "/ponni_mlp_kat.npz", w=w, x=x, y=y)
+    config4_and_thermal(tmp)
     print("golden fixtures written to", HERE)
 
 

@@ -53,6 +53,21 @@ def test_host_headers_keep_the_reference_names():
     assert "set_column" in src["column_nudging.h"] and "nudge_to_column" in src["column_nudging.h"]
 
 
+def test_host_city_headers_keep_the_reference_names():
+    """experiments/simple_city custom modules: same struct / method names and defaults as the reference's"""
+    h = open(os.path.join(HOST, "horizontal_sponge.h")).read()
+    assert "struct Horizontal_Sponge" in h and "namespace custom_modules" in h
+    assert "void init(core::Coupler &coupler, int sponge_cells = 10, real time_scale = 1)" in h
+    assert "void apply(core::Coupler &coupler, real dt, bool x1 = true, bool x2 = true, bool y1 = true, bool y2 = true)" in h
+    for f in ["override_rho_d", "override_uvel", "override_vvel", "override_wvel", "override_temp", "override_rho_v"]:
+        assert f in h
+    t = open(os.path.join(HOST, "time_averager.h")).read()
+    assert "struct Time_Averager" in t and "void accumulate(core::Coupler &coupler, real dt)" in t and "finalize" in t
+    d = open(os.path.join(HOST, "dynamics_euler_stratified_wenofv.h")).read()
+    for case in ["supercell", "thermal", "city", "building"]:
+        assert '"%s"' % case in d
+
+
 def _run(exe, yaml, steps, tmp, nranks=1, port=29731):
     dump = os.path.join(tmp, "state.bin")
     procs = []
@@ -107,3 +122,22 @@ def test_host_driver_two_ranks_matches_reference_fixture(tmp_path):
         raw = np.fromfile(dump + ".%d" % r)
         out[:, :, jb:je, :] = raw[:nf * nz * (je - jb) * nx].reshape(nf, nz, je - jb, nx)
     _compare(out, g["s1"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("yaml,gold", [("input_building.yaml", "building_city_loop6.npz"), ("input_city.yaml", "city_loop4.npz")])
+def test_host_city_driver_matches_reference_fixture(tmp_path, yaml, gold):
+    """BASELINE config 4: the simple_city driver (own building / city init incl. the RNG-drawn heights, Horizontal_Sponge,
+    immersed-boundary dycore, sponge_layer(1), Time_Averager) against the compiled reference's fixture"""
+    build_driver()
+    exe = os.path.join(HOST, "driver_city")
+    g = np.load(os.path.join(GOLD, gold))
+    steps = int(g["steps"])
+    dump, meta = _run(exe, os.path.join(GOLD, yaml), steps, str(tmp_path))
+    assert meta["steps"] == steps and meta["launches"] > 0
+    nf, nz, ny, nx = g["s1"].shape
+    raw = np.fromfile(dump).reshape(13, nz, ny, nx)
+    _compare(raw[:6], g["s1"])
+    assert np.array_equal(raw[6], g["imm"])
+    tavg = raw[7:]
+    assert np.isfinite(tavg).all() and abs(tavg[1].mean() - 20.0) < 1.0      # time-mean u stays near the 20 m/s inflow

@@ -107,3 +107,71 @@ def test_ponni_mlp_kat(golden):
     g = golden("ponni_mlp_kat.npz")
     y = O.mlp_forward(g["w"], g["x"])
     assert np.abs(y - g["y"]).max() <= 1e-6                          # ponni's own unit-test tolerance
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# init_data = thermal / building / city and the simple_city step loop (BASELINE config 4)
+# ----------------------------------------------------------------------------------------------------------------
+def city_step(p, g, f, col, dt):
+    """experiments/simple_city/driver.cpp:72-74: horiz_sponge.apply(x1,x2) -> dycore -> sponge_layer(time_scale 1)"""
+    O.horizontal_sponge(f, col, dt, 10, 1.0, (True, True, False, False))
+    O.dycore_step(p, g["bg"], f, dt, immersed=g["imm"])
+    O.sponge(f, p.dz, float(g["zlen"]), dt, 1.0)
+
+
+def test_init_thermal_and_dycore(golden):
+    for name in ("thermal_dycore5.npz", "thermal2d_dycore5.npz"):
+        g = golden(name)
+        p = params_from(g, 1)
+        f, bg = O.init_thermal(p, float(g["xlen"]), float(g["ylen"]))
+        assert relmax(bg, g["bg"]) <= 1e-15
+        for l in range(6):
+            assert relmax(f[l], g["s0"][l]) <= 1e-14, (name, l)
+        assert f[5].max() > 1e-3 and f[4].max() - f[4].min() > 1.0      # the bubble is there
+        f = g["s0"].copy()
+        O.dycore_step(p, g["bg"], f, float(g["dt"]), steps=int(g["steps"]))
+        for l in range(6):
+            assert relmax(f[l], g["s1"][l]) <= 1e-13, (name, l)
+
+
+def test_init_building(golden):
+    g = golden("building_dycore6.npz")
+    p = params_from(g, 1, use_immersed=True, enable_gravity=False)
+    f, bg, imm = O.init_uniform_flow(p, float(g["xlen"]), float(g["ylen"]))
+    assert np.array_equal(imm, g["imm"]) and imm.sum() > 0
+    assert np.array_equal(bg, g["bg"])
+    for l in range(6):
+        assert relmax(f[l], g["s0"][l]) <= 1e-15, l
+    f = g["s0"].copy()
+    O.dycore_step(p, g["bg"], f, float(g["dt"]), immersed=g["imm"], steps=int(g["steps"]))
+    for l in range(6):
+        assert relmax(f[l], g["s1"][l]) <= 1e-13, l
+
+
+def test_simple_city_loop_building(golden):
+    g = golden("building_city_loop6.npz")
+    p = params_from(g, 1, use_immersed=True, enable_gravity=False)
+    f = g["s0"].copy()
+    col = np.ascontiguousarray(f[:, :, 0, 0])
+    for _ in range(int(g["steps"])):
+        city_step(p, g, f, col, float(g["dt"]))
+    for l in range(6):
+        assert relmax(f[l], g["s1"][l]) <= 1e-13, l
+
+
+def test_init_city_and_loop(golden):
+    g = golden("city_loop4.npz")
+    p = params_from(g, 1, use_immersed=True, enable_gravity=True)
+    cpb, nby, nbx = O.city_layout(float(g["xlen"]), float(g["ylen"]), int(g["nx"]))
+    assert g["heights"].shape == (nby, nbx)
+    f, bg, imm = O.init_uniform_flow(p, float(g["xlen"]), float(g["ylen"]), city=True, heights=g["heights"])
+    assert np.array_equal(imm, g["imm"]) and imm.sum() > 0
+    assert relmax(bg, g["bg"]) <= 1e-15
+    for l in range(6):
+        assert relmax(f[l], g["s0"][l]) <= 1e-14, l
+    f = g["s0"].copy()
+    col = np.ascontiguousarray(f[:, :, 0, 0])
+    for _ in range(int(g["steps"])):
+        city_step(p, g, f, col, float(g["dt"]))
+    for l in range(6):
+        assert relmax(f[l], g["s1"][l]) <= 1e-13, l
