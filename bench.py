@@ -168,6 +168,95 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_config3(args):
+    """BASELINE configs[2], weak-scaling form: supercell + Kessler microphysics (+ sponge layer + column
+    nudging, the canonical step loop of experiments/supercell_example/driver.cpp:66-79) on 1024 x 1024 x 128 fp64 cells
+    per GPU, N = 8 variables.  Prints one extra JSON report line: full-step and dycore-only cell-updates/s."""
+    import torch
+    import torch.distributed as dist
+    import miniweatherml_b200 as mw
+    from miniweatherml_b200.supercell import supercell_column
+    from miniweatherml_b200 import distributed as mwd
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    nxl = int(os.environ.get("MW_C3_NX", "1024")); nyl = int(os.environ.get("MW_C3_NY", "1024")); nz = NZ
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        comm = mwd.create_comm(dist, rank, world, dev)
+    npx, npy, px, py = decomposition(world, rank)
+    nxg, nyg = nxl * npx, nyl * npy
+    T = 3
+    cfg = mw.make_config(nxl, nyl, nz, nxg * DX, nyg * DX, ZLEN, T, nx_glob=nxg, ny_glob=nyg, i_beg=px * nxl,
+                         j_beg=py * nyl, nproc_x=npx, nproc_y=npy, px=px, py=py)
+    dy = mw.Dycore(cfg)
+    if comm is not None:
+        dy.attach_comm(comm)
+    bg, col = supercell_column(nz, ZLEN)
+    dy.set_background(bg)
+    names = ["density_dry", "uvel", "vvel", "wvel", "temp", "water_vapor"]
+    fields = [torch.tensor(col[n], device=dev)[:, None, None].expand(nz, nyl, nxl).contiguous() for n in names]
+    fields += [torch.zeros((nz, nyl, nxl), device=dev, dtype=torch.float64) for _ in range(2)]
+    precl = torch.zeros((nyl, nxl), device=dev, dtype=torch.float64)
+    f5 = [fields[0], fields[1], fields[2], fields[4], fields[5]]
+    column = mw.column_average(f5, nxy_glob=nxg * nyg, comm=comm)
+    mw.perturb_temperature(fields[4], px * nxl, py * nyl, DX, DX, ZLEN / nz, nxg * DX, nyg * DX)
+    dt = dy.compute_time_step()
+    dz = ZLEN / nz
+    dy.enable_timing(True)
+
+    def step():
+        dy.time_step(fields, dt)
+        mw.kessler_step(fields[4], fields[0], fields[5], fields[6], fields[7], precl, dz, dt, comm=comm)
+        mw.sponge_layer(fields, dz, ZLEN, dt, nxy_glob=nxg * nyg, comm=comm)
+        mw.nudge_to_column(f5, column, dt, nxy_glob=nxg * nyg, comm=comm)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    s_ms, s_n, dyc_ms = dy.last_timing()
+    t = torch.tensor([e0.elapsed_time(e1), dyc_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, dyc_ms = t.tolist()
+    finite = all(bool(torch.isfinite(f).all()) for f in fields)
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        cells = nxg * nyg * nz
+        full = cells * args.steps / (ms * 1e-3)
+        dyc = cells / (dyc_ms * 1e-3)
+        bytes_full = 64 * 8 + 72           # SURVEY 8(d): dycore 64 N (N = 8) + Kessler 72 B per cell
+        print(json.dumps({
+            "report": "config3", "metric": "cell-updates/s per SSPRK3 step", "unit": "cell-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "value": full, "ms_per_step": ms / args.steps,
+            "dycore_only_value": dyc, "dycore_ms_per_step": dyc_ms, "stage_kernel_ms": s_ms / max(s_n, 1),
+            "scaling": "weak", "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2] (weak form): supercell + Kessler + sponge + nudging, N=8, "
+                                   "%dx%dx%d fp64 per GPU" % (nxl, nyl, nz),
+                       "global_grid": [nxg, nyg, nz], "decomposition": "%dx%d (x,y)" % (npx, npy), "dt": dt,
+                       "state_finite": finite},
+            "hbm_frac_full_step": full / world * bytes_full / 1e9 / peak,
+            "hbm_frac_dycore": dyc / world * 64 * 8 / 1e9 / peak, "peak": peak, "peak_source": peak_src,
+            "mem_gb": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
+    dy.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,7 +265,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+                    help="config2 (default, the contract line): dry dycore 512x512x128 per GPU; config3: supercell + Kessler "
+                         "+ sponge + nudging (N=8), 1024x1024x128 per GPU (SURVEY 8(d) weak-scaling size), extra report line")
     args = ap.parse_args()
+    if args.workload == "config3" and args.impl != "reference":
+        return run_config3(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
