@@ -128,6 +128,9 @@ struct mw_dycore {
   cudaStream_t cs = nullptr, cs2 = nullptr;                // exchange stream; second compute stream for the boundary tiles
   cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_prev = nullptr, ev_bnd = nullptr;
   bool overlap = false, halo_inflight = false;
+  // slab-pipelined host step (mw_dycore_time_step_host): upload / compute / download streams and per-slab events
+  cudaStream_t s_up = nullptr, s_cmp = nullptr, s_dn = nullptr;
+  std::vector<cudaEvent_t> ev_up, ev_done;
   // timing
   bool timing = false;
   std::vector<cudaEvent_t> ev;         // [0]=step begin, [1]=step end, then pairs per stage kernel
@@ -257,6 +260,9 @@ extern "C" int mw_dycore_destroy(mw_dycore *h) {
   if (h->dev_fields_alloc) for (int f = 0; f < h->N; ++f) cudaFree(h->dev_fields[f]);
   for (int d = 0; d < 4; ++d) { cudaFree(h->hsend[d]); cudaFree(h->hrecv[d]); cudaFree(h->msend[d]); cudaFree(h->mrecv[d]); }
   for (auto e : h->ev) cudaEventDestroy(e);
+  for (cudaStream_t s : {h->s_up, h->s_cmp, h->s_dn}) if (s) cudaStreamDestroy(s);
+  for (auto e : h->ev_up) cudaEventDestroy(e);
+  for (auto e : h->ev_done) cudaEventDestroy(e);
   if (h->cs) cudaStreamDestroy(h->cs);
   if (h->cs2) cudaStreamDestroy(h->cs2);
   for (cudaEvent_t e : {h->ev_ready, h->ev_halo, h->ev_prev, h->ev_bnd}) if (e) cudaEventDestroy(e);
@@ -604,12 +610,210 @@ extern "C" int mw_dycore_time_step(mw_dycore *h, double *const *fields, double d
   return MW_ERR_INVALID;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Host-buffer step, slab-pipelined.  The 5+T fields are uploaded in slabs of whole tile rows along y
+// (cudaMemcpy2DAsync: nz chunks of rows per field).  The step is a chain of L operations per row --
+// coupler->dycore conversion, then per RK stage the stage kernel and the tracer finish, then dycore->coupler -- and
+// operation l on a row needs operation l-1 on the rows within 3 cells of it (stencil halo; donor-cell FCT factor).
+// So operation l trails operation l-1 by that reach (stage kernels, which work on whole 8-row tile rows, by the next
+// multiple of 8): after each slab upload, level l advances its frontier to (uploaded rows) - off[l], off = 0, 8, 9, 16,
+// 17, 24, 25, 25 with tracers.  Compute trails the upload by < 1 slab, the download (the other PCIe direction) trails
+// compute, and H2D, kernels and D2H overlap instead of adding up.  The rows next to the periodic seam (level l: off[l]
+// rows at the bottom, about as many at the top) need both ends of the domain and are
+// finished level by level after the last upload.  All kernels go to ONE compute stream in an order in which every
+// operation follows the operations it reads from (that also covers the in-place reuse of q[0], the flux / FCT scratch
+// and the periodic images); events tie that stream to the two copy streams.  Results are bit-identical to
+// mw_dycore_time_step on device-resident fields (tests/test_gpu_dycore.py::test_host_step_pipelined_bit_identical).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NT, int KIND>
+static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double dt_phys, int rows_per_slab, int ncycles) {
+  using K = WsKernel<NT, KIND>;
+  const mw_config &c = h->cfg;
+  static bool attr_set = false;
+  if (!attr_set) { MW_CUDA_OK(K::attr()); attr_set = true; }
+  const int nbx = (c.nx + 15) / 16, nby = (c.ny + 7) / 8;
+  const int S = std::max(1, c.ny / rows_per_slab);         // the last slab takes the remainder
+  // ---- the chain of operations ----
+  double dt_dyn = dt_phys / ncycles;                                       // DYC:104-108
+  struct Link { int kind, stage; };                                        // kind: 0 c2d, 1 stage kernel, 2 tracer finish, 3 d2c
+  std::vector<Link> chain;
+  chain.push_back({0, 0});
+  for (int ic = 0; ic < ncycles; ++ic)
+    for (int st = 0; st < 3; ++st) {
+      chain.push_back({1, st});
+      if (NT > 0) chain.push_back({2, st});
+    }
+  chain.push_back({3, 0});
+  const int L = (int) chain.size();
+  // Row offsets of the levels.  off[l]: how far level l trails the upload (and where it starts above the seam);
+  // cap[l]: where its sweep ends below the seam.  A stage kernel needs its input 3 rows further (stencil halo) and works
+  // on whole tile rows (multiples of 8); the tracer finish needs the stage's FCT factors 1 row further; the conversions
+  // are cell-local.  With tracers: off = 0, 8, 9, 16, 17, 24, 25, 25.
+  std::vector<int> off(L), cap(L);
+  off[0] = 0; cap[0] = c.ny;
+  for (int l = 1; l < L; ++l) {
+    if (chain[l].kind == 1)      { off[l] = ((off[l - 1] + HALO + 7) / 8) * 8; cap[l] = ((cap[l - 1] - HALO) / 8) * 8; }
+    else if (chain[l].kind == 2) { off[l] = off[l - 1] + 1;                     cap[l] = cap[l - 1] - 1; }
+    else                         { off[l] = off[l - 1];                         cap[l] = cap[l - 1]; }
+  }
+  if (cap[L - 1] - off[L - 1] < 8) return 1;                               // too few rows for this chain: caller falls back
+
+  if (!h->s_up) {
+    MW_CUDA_OK(cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+    MW_CUDA_OK(cudaStreamCreateWithFlags(&h->s_cmp, cudaStreamNonBlocking));
+    MW_CUDA_OK(cudaStreamCreateWithFlags(&h->s_dn, cudaStreamNonBlocking));
+  }
+  static const bool prof = getenv("MW_HOST_PROF") && atoi(getenv("MW_HOST_PROF")) != 0;   // timeline of the slabs to stderr
+  while ((int) h->ev_up.size() < S + 3) {
+    cudaEvent_t a, b;
+    MW_CUDA_OK(cudaEventCreateWithFlags(&a, prof ? cudaEventDefault : cudaEventDisableTiming));
+    MW_CUDA_OK(cudaEventCreateWithFlags(&b, prof ? cudaEventDefault : cudaEventDisableTiming));
+    h->ev_up.push_back(a); h->ev_done.push_back(b);
+  }
+  if (prof) MW_CUDA_OK(cudaEventRecord(h->ev_up[S + 2], h->s_up));                          // t = 0
+  const size_t row_bytes = (size_t) c.nx * 8, plane_bytes = (size_t) c.ny * row_bytes;
+  auto copy_rows = [&](int j0, int j1, bool up) -> cudaError_t {                            // rows [j0, j1) of every field
+    for (int f = 0; f < h->N; ++f) {
+      double *d = h->dev_fields[f] + (size_t) j0 * c.nx, *hp = host_fields[f] + (size_t) j0 * c.nx;
+      cudaError_t e = up ? cudaMemcpy2DAsync(d, plane_bytes, hp, plane_bytes, (size_t) (j1 - j0) * row_bytes, c.nz, cudaMemcpyHostToDevice, h->s_up)
+                         : cudaMemcpy2DAsync(hp, plane_bytes, d, plane_bytes, (size_t) (j1 - j0) * row_bytes, c.nz, cudaMemcpyDeviceToHost, h->s_dn);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  for (int s = 0; s < S; ++s) {
+    const int j0 = s * rows_per_slab, j1 = (s == S - 1) ? c.ny : j0 + rows_per_slab;
+    MW_CUDA_OK(copy_rows(j0, j1, true));
+    MW_CUDA_OK(cudaEventRecord(h->ev_up[s], h->s_up));
+  }
+
+  ConvertParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.S = base_params(h);
+  for (int f = 0; f < h->N; ++f) Q.fields[f] = h->dev_fields[f];
+  Q.R_d = c.R_d; Q.R_v = c.R_v; Q.idWV = c.idWV;
+  unsigned am = 0;
+  for (int t = 0; t < c.num_tracers; ++t) if (c.tracer_adds_mass[t]) am |= 1u << t;
+  Q.adds_mass_mask = am;
+
+  cudaStream_t cs = h->s_cmp;
+  int n_done_ev = 0;
+  // operation `l` of the chain on rows [r0, r1); r1 > ny means the two sides of the seam, rows [r0, ny) and [0, r1 - ny)
+  auto run = [&](int l, int r0, int r1) -> int {
+    if (r1 <= r0) return MW_OK;
+    const int j0 = r0, j1 = std::min(r1, c.ny), nj = j1 - j0;
+    const int ta = r0 / 8, tb = r1 > c.ny ? nby + (r1 - c.ny) / 8 : (r1 + 7) / 8;           // stage kernels: whole tile rows
+    const unsigned cgrid = (unsigned) (((long long) c.nz * nj * c.nx + 255) / 256);
+    const Link &lk = chain[l];
+    if (lk.kind == 0) {
+      ConvertParams q = Q;
+      q.S.qout = h->q[0]; q.S.jr_lo = j0; q.S.jr_n = nj;
+      k_coupler_to_dyn<NT><<<cgrid, 256, 0, cs>>>(q);
+    } else if (lk.kind == 3) {
+      ConvertParams q = Q;
+      q.S.qin = h->q[0]; q.S.jr_lo = j0; q.S.jr_n = nj;
+      k_dyn_to_coupler<NT><<<cgrid, 256, 0, cs>>>(q);
+      if (n_done_ev >= (int) h->ev_done.size()) {
+        cudaEvent_t e;
+        MW_CUDA_OK(cudaEventCreateWithFlags(&e, prof ? cudaEventDefault : cudaEventDisableTiming));
+        h->ev_done.push_back(e);
+      }
+      cudaEvent_t e = h->ev_done[n_done_ev++];
+      MW_CUDA_OK(cudaEventRecord(e, cs));
+      MW_CUDA_OK(cudaStreamWaitEvent(h->s_dn, e, 0));
+      MW_CUDA_OK(copy_rows(j0, j1, false));
+    } else {
+      StageParams P = Q.S;
+      int in_buf;
+      const int s = lk.stage;
+      if (s == 0)      { in_buf = 0; P.qout = h->q[1]; P.rk_a = 0.0;     P.rk_b = 1.0;     P.rk_cdt = dt_dyn;               P.dt_stage = dt_dyn; }
+      else if (s == 1) { in_buf = 1; P.qout = h->q[2]; P.rk_a = 3. / 4.; P.rk_b = 1. / 4.; P.rk_cdt = (1. / 4.) * dt_dyn;   P.dt_stage = (1. / 4.) * dt_dyn; }
+      else             { in_buf = 2; P.qout = h->q[0]; P.rk_a = 1. / 3.; P.rk_b = 2. / 3.; P.rk_cdt = (2. / 3.) * dt_dyn;   P.dt_stage = (2. / 3.) * dt_dyn; }
+      P.qin = h->q[in_buf];
+      P.q0 = h->q[0];
+      if (lk.kind == 1 && tb > nby) {
+        // seam: tile rows [ta, nby) and [0, tb - nby) = every tile outside the rectangle of rows [tb - nby, ta) (tile_mode 2)
+        P.tile_mode = 2; P.nbx = nbx; P.nby = nby; P.tbx_lo = 0; P.tbx_hi = nbx; P.tby_lo = tb - nby; P.tby_hi = ta;
+        K::launch(dim3(nbx * (tb - ta)), cs, h->tmap[in_buf], P);
+      } else if (lk.kind == 1) {
+        P.tile_mode = 1; P.nbx = nbx; P.nby = nby; P.tbx_lo = 0; P.tbx_hi = nbx; P.tby_lo = ta; P.tby_hi = tb;
+        K::launch(dim3(nbx * (tb - ta)), cs, h->tmap[in_buf], P);
+      } else {
+        P.jr_lo = j0; P.jr_n = nj;
+        k_tracer_update<NT><<<cgrid, 256, 0, cs>>>(P);
+      }
+    }
+    h->launches++;
+    return MW_OK;
+  };
+
+  std::vector<int> hi(off);                                                // level l starts at row off[l]
+  for (int s = 0; s < S; ++s) {
+    MW_CUDA_OK(cudaStreamWaitEvent(cs, h->ev_up[s], 0));
+    const bool last = (s == S - 1);
+    const int u = last ? c.ny : (s + 1) * rows_per_slab;                   // rows uploaded so far
+    for (int l = 0; l < L; ++l) {
+      const int nh = last ? cap[l] : std::min(u - off[l], cap[l]);
+      if (nh > hi[l]) { int rc = run(l, hi[l], nh); if (rc != MW_OK) return rc; hi[l] = nh; }
+    }
+  }
+  for (int l = 1; l < L; ++l) {                                            // the seam region, level by level
+    int rc = MW_OK;
+    if (chain[l].kind == 1) rc = run(l, cap[l], c.ny + off[l]);            // stage kernel: both sides in one launch
+    else { rc = run(l, cap[l], c.ny); if (rc == MW_OK) rc = run(l, 0, off[l]); }
+    if (rc != MW_OK) return rc;
+  }
+  MW_CUDA_OK(cudaGetLastError());
+  if (prof) MW_CUDA_OK(cudaEventRecord(h->ev_up[S + 1], h->s_dn));
+  MW_CUDA_OK(cudaStreamSynchronize(h->s_dn));
+  MW_CUDA_OK(cudaStreamSynchronize(cs));
+  MW_CUDA_OK(cudaStreamSynchronize(h->s_up));
+  if (prof) {
+    float t = 0;
+    fprintf(stderr, "[mw host pipeline] %d slabs of %d rows, chain of %d operations; ms since the first upload was queued\n  uploaded:", S, rows_per_slab, L);
+    for (int p2 = 0; p2 < S; ++p2) { cudaEventElapsedTime(&t, h->ev_up[S + 2], h->ev_up[p2]); fprintf(stderr, " %.1f", t); }
+    fprintf(stderr, "\n  converted back (download queued behind):");
+    for (int s2 = 0; s2 < n_done_ev; ++s2) { cudaEventElapsedTime(&t, h->ev_up[S + 2], h->ev_done[s2]); fprintf(stderr, " %.1f", t); }
+    cudaEventElapsedTime(&t, h->ev_up[S + 2], h->ev_up[S + 1]);
+    fprintf(stderr, "\n  last download done: %.1f\n", t);
+  }
+  return MW_OK;
+}
+
 extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields, double dt_phys) {
   MW_REQUIRE(h && host_fields, "mw_dycore_time_step_host: null argument");
-  const size_t bytes = (size_t) h->cfg.nz * h->cfg.ny * h->cfg.nx * 8;
+  MW_REQUIRE(h->bg_set, "mw_dycore_time_step_host: background profiles not set");
+  MW_REQUIRE(dt_phys > 0, "mw_dycore_time_step_host: dt_phys = %g", dt_phys);
+  const mw_config &c = h->cfg;
+  const size_t bytes = (size_t) c.nz * c.ny * c.nx * 8;
   if (!h->dev_fields_alloc) {
     for (int f = 0; f < h->N; ++f) MW_CUDA_OK(cudaMalloc(&h->dev_fields[f], bytes));
     h->dev_fields_alloc = true;
+  }
+  // slab pipeline: single rank, 3-D, the warp-specialised stage kernel, and enough rows for >= 6 slabs of whole tile
+  // rows with about one wave of tiles (148 SMs, one CTA each) per slab launch.  MW_HOST_SLAB_ROWS overrides (0 = off).
+  int rows_per_slab = 0;
+  {
+    const int nbx = (c.nx + 15) / 16;
+    int tile_rows = std::max(1, 148 / nbx);
+    rows_per_slab = 8 * tile_rows;
+    const char *e = getenv("MW_HOST_SLAB_ROWS");
+    if (e) rows_per_slab = (atoi(e) / 8) * 8;
+  }
+  const int variant = tile_variant(c.num_tracers);
+  const int ncycles = (int) ceil(dt_phys / mw_dycore_compute_time_step(h));                 // DYC:104-108
+  const bool pipelined = rows_per_slab >= 8 && c.nproc_x * c.nproc_y == 1 && !h->comm && c.ny_glob > 1 && variant == 2 &&
+                         c.ny / rows_per_slab >= 4;
+  if (pipelined) {
+    MW_CUDA_OK(cudaDeviceSynchronize());                  // the non-blocking streams do not order against earlier default-stream work
+    int rc = 1;
+    switch (c.num_tracers) {
+      case 0: rc = host_step_pipelined<0, 2>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
+      case 1: rc = host_step_pipelined<1, 2>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
+      case 2: rc = host_step_pipelined<2, 2>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
+      case 3: rc = host_step_pipelined<3, 2>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
+    }
+    if (rc != 1) return rc;                               // 1 = grid too small for the chain: unpipelined path below
   }
   for (int f = 0; f < h->N; ++f) MW_CUDA_OK(cudaMemcpyAsync(h->dev_fields[f], host_fields[f], bytes, cudaMemcpyHostToDevice, 0));
   int rc = mw_dycore_time_step(h, h->dev_fields, dt_phys, nullptr);

@@ -45,6 +45,9 @@ struct StageParams {
   // which tiles a launch covers (halo exchange overlapped with interior compute): 0 = all (2-D grid), 1 = the interior
   // rectangle [tbx_lo,tbx_hi) x [tby_lo,tby_hi) of tiles, 2 = every tile outside it (1-D grids); nbx = tiles per row
   int tile_mode, tbx_lo, tbx_hi, tby_lo, tby_hi, nbx, nby;
+  // row range [jr_lo, jr_lo + jr_n) covered by one launch of the cell-wise kernels (k_tracer_update, k_coupler_to_dyn,
+  // k_dyn_to_coupler) in the slab-pipelined host step; jr_n == 0 = every row
+  int jr_lo, jr_n;
   // optional in-kernel wait accounting (MW_STAGE_PROF=1, k_stage_uj only): cycles summed over one probe thread per role
   // and CTA: [0] R total, [1] R waiting for U (empty), [2] R waiting for TMA, [3] U total, [4] U waiting for R (full),
   // [5] U in its named barriers, [6] CTAs
@@ -72,6 +75,17 @@ __device__ __forceinline__ void tile_coords(const StageParams &P, int &bx, int &
 // --------------------------------------------------------------------------------------------------------
 // small helpers
 // --------------------------------------------------------------------------------------------------------
+// thread -> cell of the launch's row range; false when out of range.  c = flat index in the full [nz][ny][nx] array
+__device__ __forceinline__ bool range_cell(const StageParams &P, int &k, int &j, int &i, long long &c) {
+  const int nyr = P.jr_n > 0 ? P.jr_n : P.ny;
+  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long) P.nz * nyr * P.nx) return false;
+  i = (int) (t % P.nx);
+  j = P.jr_lo + (int) ((t / P.nx) % nyr);
+  k = (int) (t / ((long long) P.nx * nyr));
+  c = ((long long) k * P.ny + j) * P.nx + i;
+  return true;
+}
 __device__ __forceinline__ void store_with_images(double *var_base, const StageParams &P, int k, int j, int i,
                                                   double v) {
   double *row = var_base + (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + HALO;
@@ -653,9 +667,9 @@ k_stage(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
 template <int NT>
 __global__ void __launch_bounds__(256) k_tracer_update(const StageParams P) {
   const long long ncell = (long long) P.nz * P.ny * P.nx;
-  const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncell) return;
-  const int i = (int) (c % P.nx), j = (int) ((c / P.nx) % P.ny), k = (int) (c / ((long long) P.nx * P.ny));
+  int i, j, k;
+  long long c;
+  if (!range_cell(P, k, j, i, c)) return;
   const long long hcell = (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + i + HALO;
   const double rho_new = P.qout[hcell] + __ldg(P.hyc + k);
   const long long pl = (long long) P.ny * P.nx;
@@ -701,10 +715,9 @@ struct ConvertParams {
 template <int NT>
 __global__ void __launch_bounds__(256) k_coupler_to_dyn(const ConvertParams Q) {
   const StageParams &P = Q.S;
-  const long long ncell = (long long) P.nz * P.ny * P.nx;
-  const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncell) return;
-  const int i = (int) (c % P.nx), j = (int) ((c / P.nx) % P.ny), k = (int) (c / ((long long) P.nx * P.ny));
+  int i, j, k;
+  long long c;
+  if (!range_cell(P, k, j, i, c)) return;
   const double rho_d = Q.fields[0][c], u = Q.fields[1][c], v = Q.fields[2][c], w = Q.fields[3][c], temp = Q.fields[4][c];
   double trv[NT > 0 ? NT : 1];
   double rho = rho_d;
@@ -732,10 +745,9 @@ __global__ void __launch_bounds__(256) k_coupler_to_dyn(const ConvertParams Q) {
 template <int NT>
 __global__ void __launch_bounds__(256) k_dyn_to_coupler(const ConvertParams Q) {
   const StageParams &P = Q.S;
-  const long long ncell = (long long) P.nz * P.ny * P.nx;
-  const long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncell) return;
-  const int i = (int) (c % P.nx), j = (int) ((c / P.nx) % P.ny), k = (int) (c / ((long long) P.nx * P.ny));
+  int i, j, k;
+  long long c;
+  if (!range_cell(P, k, j, i, c)) return;
   const long long h = (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + i + HALO;
   const double *q = P.qin;
   const double rho = q[h] + __ldg(P.hyc + k);
