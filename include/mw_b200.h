@@ -153,6 +153,12 @@ int  mw_surrogate_forward(long long n, const float *weights, const double *scl_i
 int  mw_mlp_forward(long long B, const float *weights /*host*/, const float *x, float *y, int use_tensor_cores,
                     void *stream);
 
+/* general Dense(nin->nh) + LeakyReLU(negative_slope) + Dense(nh->nout) in fp32 with ponni's operation order (the model family
+ * of ponni's own known-answer test, external/ponni/unit/keras_sequential/test_keras_sequential.cpp:11-50); widths <= 64.
+ * weights: HOST W1[nin][nh], b1[nh], W2[nh][nout], b2[nout] (Keras "kernel:0" is [in][out]); x device [nin][B], y device [nout][B] */
+int  mw_mlp_dense2_forward(long long B, int nin, int nh, int nout, float negative_slope, const float *weights,
+                           const float *x, float *y, void *stream);
+
 /* ---- the other calls of the canonical step loop ---------------------------------------------------------- */
 int  mw_sponge_layer(int nfields, double *const *fields, int nz, int ny, int nx, long long nx_glob_ny_glob,
                      double dz, double zlen, double dt, double time_scale, mw_comm *comm, void *stream);

@@ -248,3 +248,64 @@ extern "C" int mw_surrogate_forward(long long n, const float *weights, const dou
   MW_CUDA_OK(cudaGetLastError());
   return MW_OK;
 }
+
+// ---- general Dense -> LeakyReLU -> Dense (any widths up to 64), fp32, ponni's operation order ------------------------
+// The network family ponni's own known-answer test uses (external/ponni/unit/keras_sequential/test_keras_sequential.cpp:
+// 11-50: Dense(12->10) + LeakyReLU(0.1) + Dense(10->4), the 3-cell-stencil surrogate).  Weights sit in shared memory,
+// one thread per sample, hidden activations in registers.
+namespace mw {
+constexpr int MLP_MAXW = 64;
+struct Dense2Params {
+  const float *w;           // device: W1[nin][nh], b1[nh], W2[nh][nout], b2[nout]
+  const float *x;           // [nin][B]
+  float *y;                 // [nout][B]
+  long long B;
+  int nin, nh, nout;
+  float slope;
+};
+__global__ void __launch_bounds__(128) k_mlp_dense2(const Dense2Params P) {
+  extern __shared__ float sw[];
+  const int nw = P.nin * P.nh + P.nh + P.nh * P.nout + P.nout;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = P.w[i];
+  __syncthreads();
+  const float *W1 = sw, *b1 = W1 + P.nin * P.nh, *W2 = b1 + P.nh, *b2 = W2 + P.nh * P.nout;
+  const long long b = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  float h[MLP_MAXW];
+#pragma unroll 1
+  for (int r = 0; r < P.nh; ++r) {
+    float t = 0.f;
+    for (int k = 0; k < P.nin; ++k) t = __fadd_rn(t, __fmul_rn(W1[k * P.nh + r], P.x[(long long) k * P.B + b]));   // ponni_Matvec.h:68-72
+    t = __fadd_rn(t, b1[r]);                                                                                       // ponni_Bias.h:66
+    if (t < 0.f) t = __fmul_rn(t, P.slope);                                                                        // ponni_Relu.h:56
+    h[r] = t;
+  }
+#pragma unroll 1
+  for (int r = 0; r < P.nout; ++r) {
+    float t = 0.f;
+    for (int k = 0; k < P.nh; ++k) t = __fadd_rn(t, __fmul_rn(W2[k * P.nout + r], h[k]));
+    P.y[(long long) r * P.B + b] = __fadd_rn(t, b2[r]);
+  }
+}
+}  // namespace mw
+
+extern "C" int mw_mlp_dense2_forward(long long B, int nin, int nh, int nout, float negative_slope, const float *weights,
+                                     const float *x, float *y, void *stream) {
+  int rc = device_check_cached();
+  if (rc != MW_OK) return rc;
+  MW_REQUIRE(weights && x && y && B >= 0, "mw_mlp_dense2_forward: bad argument");
+  MW_REQUIRE(nin >= 1 && nin <= MLP_MAXW && nh >= 1 && nh <= MLP_MAXW && nout >= 1 && nout <= MLP_MAXW,
+             "mw_mlp_dense2_forward: widths %d -> %d -> %d (each must be 1..%d)", nin, nh, nout, MLP_MAXW);
+  if (B == 0) return MW_OK;
+  const size_t nw = (size_t) nin * nh + nh + (size_t) nh * nout + nout;
+  cudaStream_t st = (cudaStream_t) stream;
+  float *dw = nullptr;
+  MW_CUDA_OK(cudaMallocAsync(&dw, nw * sizeof(float), st));
+  MW_CUDA_OK(cudaMemcpyAsync(dw, weights, nw * sizeof(float), cudaMemcpyHostToDevice, st));
+  Dense2Params P{dw, x, y, B, nin, nh, nout, negative_slope};
+  k_mlp_dense2<<<(unsigned) ((B + 127) / 128), 128, nw * sizeof(float), st>>>(P);
+  MW_CUDA_OK(cudaGetLastError());
+  MW_CUDA_OK(cudaStreamSynchronize(st));                      // `weights` is a pageable host buffer of the caller
+  MW_CUDA_OK(cudaFreeAsync(dw, st));
+  return MW_OK;
+}

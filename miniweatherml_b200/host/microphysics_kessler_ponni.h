@@ -3,11 +3,13 @@
 // 5 -> 10 -> LeakyReLU(0.1) -> 4 (fp32) evaluated next to the real Kessler scheme.  Like the reference it prints
 // the mean differences (PON:266-269); unlike the reference's commented-out lines (PON:271-276) the overwrite of the
 // state by the network output is a run-time switch (`replace_with_surrogate`).
-// Weights: `nn_weights_raw` (104 little-endian fp32: W1[5][10], b1[10], W2[10][4], b2[4]) or, absent that key,
-// random-init std::mt19937(1234) uniform(-0.5,0.5) as BASELINE config 5 specifies (HDF5 is not available here, so
-// the shipped Keras .h5 cannot be read).
+// Weights, in this order of precedence: `keras_weights_h5` (the reference's key, PON:99; datasets
+// /dense_6/dense_6/{kernel:0,bias:0} and /dense_7/dense_7/{kernel:0,bias:0} as at PON:104-108, read by the minimal HDF5
+// reader in mw_h5.h since libhdf5 is absent here), `nn_weights_raw` (104 little-endian fp32: W1[5][10], b1[10],
+// W2[10][4], b2[4]), else random-init std::mt19937(1234) uniform(-0.5,0.5) as BASELINE config 5 specifies.
 #pragma once
 #include "microphysics_kessler.h"
+#include "mw_h5.h"
 #include <random>
 
 namespace custom_modules {
@@ -25,18 +27,32 @@ class Microphysics_Kessler : public modules::Microphysics_Kessler {
 
   void init(core::Coupler &coupler) {                               // PON:61-146
     modules::Microphysics_Kessler::init(coupler);
-    std::string w_file, in_file, out_file;
+    std::string w_file, h5_file, in_file, out_file;
     if (coupler.option_exists("standalone_input_file")) {
       YAML::Node config = YAML::LoadFile(coupler.get_option<std::string>("standalone_input_file"));
       if (config) {
         w_file = config["nn_weights_raw"].as<std::string>("");
+        h5_file = config["keras_weights_h5"].as<std::string>("");
         in_file = config["nn_input_scaling"].as<std::string>("");
         out_file = config["nn_output_scaling"].as<std::string>("");
         replace_with_surrogate = config["replace_with_surrogate"].as<bool>(false);
         use_tensor_cores = config["surrogate_tensor_cores"].as<bool>(true);
       }
     }
-    if (!w_file.empty()) {
+    if (!h5_file.empty()) {                                         // PON:104-108
+      try {
+        mw::H5File h5(h5_file);
+        char const *ds[4] = {"/dense_6/dense_6/kernel:0", "/dense_6/dense_6/bias:0", "/dense_7/dense_7/kernel:0", "/dense_7/dense_7/bias:0"};
+        std::vector<std::vector<size_t>> want = {{5, 10}, {10}, {10, 4}, {4}};
+        size_t o = 0;
+        for (int i = 0; i < 4; ++i) {
+          std::vector<size_t> shape;
+          auto v = h5.read_f32(ds[i], shape);
+          if (shape != want[i]) endrun(std::string("ERROR: ") + ds[i] + " in " + h5_file + " does not have the 5->10->4 network's shape");
+          for (auto x : v) weights[o++] = x;
+        }
+      } catch (std::runtime_error const &e) { endrun(e.what()); }
+    } else if (!w_file.empty()) {
       std::ifstream f(w_file, std::ios::binary);
       if (!f || !f.read((char *) weights, sizeof(weights))) endrun("ERROR: cannot read 104 fp32 weights from " + w_file);
     } else {

@@ -76,6 +76,7 @@ def lib():
         _lib.mwo_kessler_step.argtypes = [C.c_int, C.c_int] + [C.c_double] * 6 + [dp] * 6
         fp = C.POINTER(C.c_float)
         _lib.mwo_mlp_forward.argtypes = [C.c_int, fp, fp, fp]
+        _lib.mwo_mlp_dense2.argtypes = [C.c_int] * 4 + [C.c_float, fp, fp, fp]
         _lib.mwo_surrogate.argtypes = [C.c_size_t, fp, dp, dp] + [dp] * 9
         _lib.mwo_sponge.argtypes = [C.c_int] * 4 + [C.c_double] * 4 + [dp]
         pp = C.POINTER(dp)
@@ -142,6 +143,16 @@ def mlp_forward(w, x):
     B = x.shape[1]
     y = np.empty((4, B), dtype=np.float32)
     lib().mwo_mlp_forward(B, _fp(w), _fp(x), _fp(y))
+    return y
+
+
+def mlp_dense2(w, x, nh, nout, slope=0.1):
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    nin, B = x.shape
+    assert w.size == nin * nh + nh + nh * nout + nout
+    y = np.empty((nout, B), dtype=np.float32)
+    lib().mwo_mlp_dense2(B, nin, nh, nout, slope, _fp(w), _fp(x), _fp(y))
     return y
 
 

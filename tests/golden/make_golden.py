@@ -64,10 +64,43 @@ def config4_and_thermal(tmp):
                         enable_gravity=1, **g)
 
 
+def keras_weight_fixtures(tmp):
+    """(1) ponni's own known-answer test, the only golden vector the reference holds on this path
+    (external/ponni/unit/keras_sequential/test_keras_sequential.cpp:11-50): Dense(12->10) + LeakyReLU(0.1) + Dense(10->4)
+    with the weights of keras_sequential_data.h5, one input sample, four expected outputs, tolerance 1e-6.
+    (2) the surrogate experiment's shipped trained weights and scaling tables
+    (experiments/supercell_kessler_surrogate/inputs/examples/), pushed through the compiled ponni layers."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from miniweatherml_b200.h5min import H5Min, keras_mlp_weights
+    ref = os.environ.get("MW_REFERENCE", "/root/reference")
+    f = ref + "/external/ponni/unit/keras_sequential/keras_sequential_data.h5"
+    w = keras_mlp_weights(f, layers=("dense", "dense_1"))
+    x = np.array([5.08810276e-01, 4.78929254e-01, 4.54260898e-01, 6.02555739e-02, 4.85583159e-02, 3.79940443e-02,
+                  1.20564349e-04, 6.27402543e-04, 3.41872996e-03, 1.34502158e-03, 4.29940776e-04, 6.08758314e-06],
+                 dtype=np.float32)[:, None]                                  # test_keras_sequential.cpp:24-35
+    y = np.array([4.7658795e-01, 4.8446856e-02, 1.2472458e-03, 4.0419400e-05], dtype=np.float32)[:, None]   # :44-47
+    np.savez_compressed(HERE + "/keras_sequential_kat.npz", w=w, x=x, y=y, nin=12, nh=10, nout=4, slope=0.1, tol=1e-6,
+                        members=np.array(H5Min(f).list("/")))
+    ex = ref + "/experiments/supercell_kessler_surrogate/inputs/examples/"
+    w = keras_mlp_weights(ex + "supercell_kessler_singlecell_model_weights.h5")
+    rng = np.random.default_rng(77)
+    x = rng.uniform(-0.1, 1.1, (5, 512)).astype(np.float32)
+    w.astype(np.float64).tofile(tmp + "/w.bin")
+    x.astype(np.float64).tofile(tmp + "/x.bin")
+    subprocess.check_call([O.REF_DRIVER, "mlp", "512", tmp + "/w.bin", tmp + "/x.bin", tmp + "/y.bin"], stdout=subprocess.DEVNULL)
+    y = np.fromfile(tmp + "/y.bin").reshape(4, 512).astype(np.float32)
+    np.savez_compressed(HERE + "/ponni_shipped_weights_kat.npz", w=w, x=x, y=y,
+                        scl_in=np.loadtxt(ex + "supercell_kessler_stencil_input_scaling.txt"),
+                        scl_out=np.loadtxt(ex + "supercell_kessler_stencil_output_scaling.txt"))
+
+
 def main():
     tmp = tempfile.mkdtemp()
     if "--config4" in sys.argv:
         config4_and_thermal(tmp)
+        return
+    if "--keras" in sys.argv:
+        keras_weight_fixtures(tmp)
         return
     # --- config 1: shipped supercell_example grid (100 x 1 x 40, 2-D), Kessler tracers -----------------------
     g = dict(nx=100, ny=1, nz=40, xlen=1e5, ylen=1e5, zlen=2e4)
@@ -141,6 +174,7 @@ def main():
     y = np.fromfile(tmp + "/y.bin").reshape(4, 256).astype(np.float32)
     np.savez_compressed(HERE + "/ponni_mlp_kat.npz", w=w, x=x, y=y)
     config4_and_thermal(tmp)
+    keras_weight_fixtures(tmp)
     print("golden fixtures written to", HERE)
 
 

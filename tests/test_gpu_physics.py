@@ -193,3 +193,52 @@ def test_init_supercell_vs_reference_initial_state(golden):
         for l in range(5 + T):
             assert relmax(f[l].cpu().numpy(), s0[l]) <= 1e-12, (name, l)
         dy.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# general Dense -> LeakyReLU -> Dense kernel: ponni's own known-answer test, and the shipped trained surrogate
+# ----------------------------------------------------------------------------------------------------------------
+def test_mlp_dense2_vs_ponni_keras_sequential_kat(golden):
+    """external/ponni/unit/keras_sequential/test_keras_sequential.cpp:11-50 (12 -> 10 -> 4, four outputs within 1e-6)"""
+    import torch
+    import miniweatherml_b200 as mw
+    g = golden("keras_sequential_kat.npz")
+    y = mw.mlp_dense2_forward(g["w"], torch.tensor(g["x"], device="cuda"), 10, 4, 0.1).cpu().numpy()
+    assert np.abs(y - g["y"]).max() <= float(g["tol"])
+    assert np.array_equal(y, O.mlp_dense2(g["w"], g["x"], 10, 4, 0.1))          # same fp32 roundings as the oracle
+
+
+@pytest.mark.parametrize("nin,nh,nout,B", [(12, 10, 4, 1000), (5, 10, 4, 257), (1, 1, 1, 3), (64, 64, 64, 130), (7, 33, 2, 1)])
+def test_mlp_dense2_vs_oracle(nin, nh, nout, B):
+    import torch
+    import miniweatherml_b200 as mw
+    rng = np.random.default_rng(nin * 100 + nh)
+    w = rng.uniform(-0.5, 0.5, nin * nh + nh + nh * nout + nout).astype(np.float32)
+    x = rng.uniform(-1, 1, (nin, B)).astype(np.float32)
+    y = mw.mlp_dense2_forward(w, torch.tensor(x, device="cuda"), nh, nout, 0.1).cpu().numpy()
+    assert np.array_equal(y, O.mlp_dense2(w, x, nh, nout, 0.1))
+    with pytest.raises(mw.MwError):
+        mw.mlp_dense2_forward(np.zeros(65 * 2 + 2 + 2 + 1, dtype=np.float32), torch.zeros((65, 4), device="cuda"), 2, 1)
+
+
+@pytest.mark.parametrize("tc", [False, True])
+def test_shipped_surrogate_weights_kat(golden, tc):
+    """the experiment's trained weights (read from the Keras .h5 by the minimal HDF5 reader) through the compiled ponni
+    layers = fixture; fp32 FMA path bit-identical, tensor-core path within ponni's own 1e-6"""
+    import torch
+    import miniweatherml_b200 as mw
+    g = golden("ponni_shipped_weights_kat.npz")
+    y = mw.mlp_forward(g["w"], torch.tensor(g["x"], device="cuda"), use_tensor_cores=tc).cpu().numpy()
+    assert np.abs(y - g["y"]).max() <= 1e-6
+    if not tc:
+        assert np.array_equal(y, g["y"])
+        assert np.array_equal(mw.mlp_dense2_forward(g["w"], torch.tensor(g["x"], device="cuda"), 10, 4).cpu().numpy(), g["y"])
+    # the trained network on a real cloudy state stays close to Kessler's own tendencies' range (sanity of weights + scaling)
+    s = golden("config1_restart1000_full10.npz")["s0"]
+    fl = [np.ascontiguousarray(s[i].ravel()) for i in (4, 0, 5, 6, 7)]
+    ref = O.surrogate(g["w"], g["scl_in"], g["scl_out"], *fl)
+    out = mw.surrogate_forward(g["w"], g["scl_in"], g["scl_out"], *[dev(x) for x in fl], use_tensor_cores=tc)
+    rngs = g["scl_out"][:, 1] - g["scl_out"][:, 0]
+    for f in range(4):
+        assert np.abs(out[f].cpu().numpy() - ref[f]).max() / rngs[f] <= (1e-6 if tc else 1e-12)
+    assert np.abs(out[0].cpu().numpy() - fl[0]).max() < 5.0            # temperature after "microphysics" within 5 K of before

@@ -141,3 +141,40 @@ def test_host_city_driver_matches_reference_fixture(tmp_path, yaml, gold):
     assert np.array_equal(raw[6], g["imm"])
     tavg = raw[7:]
     assert np.isfinite(tavg).all() and abs(tavg[1].mean() - 20.0) < 1.0      # time-mean u stays near the 20 m/s inflow
+
+
+@pytest.mark.gpu
+def test_host_driver_surrogate_reads_keras_h5(tmp_path, golden):
+    """supercell_kessler_surrogate driver path: `keras_weights_h5` (the reference's key, PON:99-108) read by mw_h5.h gives
+    the same network as the same weights passed raw; the state itself follows the real Kessler scheme (PON:271-276)."""
+    from test_h5 import H5Writer
+    build_driver()
+    exe = os.path.join(HOST, "driver")
+    g = golden("ponni_shipped_weights_kat.npz")
+    w = g["w"]
+    hw = H5Writer()
+    g6 = hw.group({"kernel:0": hw.dataset(w[:50].reshape(5, 10)), "bias:0": hw.dataset(w[50:60])})
+    g7 = hw.group({"kernel:0": hw.dataset(w[60:100].reshape(10, 4)), "bias:0": hw.dataset(w[100:104])})
+    root = hw.group({"dense_6": hw.group({"dense_6": g6[0]})[0], "dense_7": hw.group({"dense_7": g7[0]})[0]})
+    open(tmp_path / "weights.h5", "wb").write(hw.finish(root))
+    w.astype("<f4").tofile(tmp_path / "weights.raw")
+    np.savetxt(tmp_path / "in.txt", g["scl_in"])
+    np.savetxt(tmp_path / "out.txt", g["scl_out"])
+    base = open(os.path.join(GOLD, "input_config1.yaml")).read()
+    outs = {}
+    for kind, line in [("h5", "keras_weights_h5: %s" % (tmp_path / "weights.h5")), ("raw", "nn_weights_raw: %s" % (tmp_path / "weights.raw"))]:
+        y = tmp_path / ("in_%s.yaml" % kind)
+        y.write_text(base + "\n%s\nnn_input_scaling: %s\nnn_output_scaling: %s\n" % (line, tmp_path / "in.txt", tmp_path / "out.txt"))
+        d = tmp_path / kind
+        d.mkdir()
+        r = subprocess.run([exe, str(y), "steps=3", "dump=" + str(d / "s.bin"), "quiet=1", "surrogate=1"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        diffs = [float(l.split(":")[1]) for l in r.stdout.splitlines() if l.startswith("Relative diff")]
+        assert len(diffs) == 12 and np.isfinite(diffs).all()
+        outs[kind] = (diffs, np.fromfile(d / "s.bin"))
+    assert outs["h5"][0] == outs["raw"][0]                            # same network either way
+    assert np.array_equal(outs["h5"][1], outs["raw"][1])
+    bad = tmp_path / "bad.yaml"
+    bad.write_text(base + "\nkeras_weights_h5: %s\n" % (tmp_path / "in.txt"))
+    r = subprocess.run([exe, str(bad), "steps=1", "quiet=1", "surrogate=1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "not an HDF5 file" in r.stderr

@@ -175,3 +175,22 @@ def test_init_city_and_loop(golden):
         city_step(p, g, f, col, float(g["dt"]))
     for l in range(6):
         assert relmax(f[l], g["s1"][l]) <= 1e-13, l
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The reference's own known-answer test on the MLP path + the shipped trained surrogate weights (read from the Keras
+# .h5 files by the minimal HDF5 reader; fixtures written by tests/golden/make_golden.py --keras)
+# ----------------------------------------------------------------------------------------------------------------
+def test_ponni_keras_sequential_kat(golden):
+    """external/ponni/unit/keras_sequential/test_keras_sequential.cpp:11-50: four outputs within 1e-6"""
+    g = golden("keras_sequential_kat.npz")
+    y = O.mlp_dense2(g["w"], g["x"], int(g["nh"]), int(g["nout"]), float(g["slope"]))
+    assert np.abs(y - g["y"]).max() <= float(g["tol"])
+    assert list(g["members"]) == ["dense", "dense_1", "leaky_re_lu", "top_level_model_weights"] or "dense" in list(g["members"])
+
+
+def test_shipped_surrogate_weights_kat(golden):
+    g = golden("ponni_shipped_weights_kat.npz")
+    assert g["w"].shape == (104,) and g["scl_in"].shape == (5, 2) and g["scl_out"].shape == (4, 2)
+    assert np.array_equal(O.mlp_forward(g["w"], g["x"]), g["y"])              # compiled ponni layers, same roundings
+    assert np.array_equal(O.mlp_dense2(g["w"], g["x"], 10, 4), g["y"])
