@@ -189,6 +189,7 @@ int  mw_time_average_accumulate(int nfields, double *const *avg, const double *c
 /* ---- communicator (NCCL over NVLink), one process per GPU -------------------------------------------------- */
 int  mw_comm_unique_id(void *id_bytes_128);                       /* rank 0 creates, caller broadcasts            */
 int  mw_comm_create(const void *id_bytes_128, int nranks, int rank, mw_comm **out);
+int  mw_comm_barrier(mw_comm *c);                                 /* MPI_Barrier: host returns when every rank arrived */
 int  mw_comm_destroy(mw_comm *c);
 
 #ifdef __cplusplus

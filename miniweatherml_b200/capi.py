@@ -84,6 +84,7 @@ def lib():
         ("mw_comm_unique_id", [vp]),
         ("mw_comm_create", [vp, C.c_int, C.c_int, C.POINTER(vp)]),
         ("mw_comm_destroy", [vp]),
+        ("mw_comm_barrier", [vp]),
     ]:
         if hasattr(L, name):
             getattr(L, name).argtypes = args

@@ -47,8 +47,17 @@ extern "C" int mw_comm_create(const void *id_bytes_128, int nranks, int rank, mw
   return MW_OK;
 }
 
+extern "C" int mw_comm_barrier(mw_comm *c) {
+  if (!c || c->nranks <= 1) return MW_OK;
+  if (!c->scratch) { MW_CUDA_OK(cudaMalloc(&c->scratch, 8)); MW_CUDA_OK(cudaMemset(c->scratch, 0, 8)); }
+  MW_NCCL_OK(ncclAllReduce(c->scratch, c->scratch, 1, ncclInt, ncclSum, c->comm, 0));
+  MW_CUDA_OK(cudaStreamSynchronize(0));
+  return MW_OK;
+}
+
 extern "C" int mw_comm_destroy(mw_comm *c) {
   if (!c) return MW_OK;
+  if (c->scratch) cudaFree(c->scratch);
   if (c->comm) ncclCommDestroy(c->comm);
   delete c;
   return MW_OK;

@@ -7,6 +7,7 @@
 struct mw_comm {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  int *scratch = nullptr;          // device word for mw_comm_barrier
 };
 
 namespace mw {

@@ -4,7 +4,10 @@
 // BASELINE.json calls this class "Dynamics_Euler_Stateless"; an alias is provided below.
 #pragma once
 #include "coupler.h"
+#include "mw_netcdf.h"
+#include <iomanip>
 #include <random>
+#include <sstream>
 
 namespace modules {
 class Dynamics_Euler_Stratified_WenoFV {
@@ -41,10 +44,17 @@ class Dynamics_Euler_Stratified_WenoFV {
     if (!handle) endrun("ERROR: Dynamics_Euler_Stratified_WenoFV::time_step called before init");
     mw::check(mw_dycore_time_step(handle, field_ptrs.data(), dt_phys, nullptr), "mw_dycore_time_step");
     etime += dt_phys;
-    if (out_freq >= 0. && etime / out_freq >= num_out + 1) {        // DYC:184-196 (output itself is out of scope)
+    if (out_freq >= 0. && etime / out_freq >= num_out + 1) {        // DYC:184-196
       yakl::fence();
+      output(coupler, etime);
       num_out++;
-      if (coupler.is_mainproc()) std::cout << "Etime , dtphys: " << std::scientific << std::setw(10) << etime << " , " << dt_phys << std::endl;
+      if (coupler.is_mainproc()) {                                  // DYC:189-195: elapsed time, dt, max |w|
+        auto w = coupler.get_data_manager_readonly().get<real const, 4>("wvel").createHostCopy();
+        real maxw = 0;
+        for (auto v : w) maxw = std::max(maxw, std::abs(v));
+        std::cout << "Etime , dtphys, maxw: " << std::scientific << std::setw(10) << etime << " , " << dt_phys << " , "
+                  << std::setw(10) << maxw << std::endl;
+      }
     }
   }
 
@@ -155,9 +165,45 @@ class Dynamics_Euler_Stratified_WenoFV {
     mw::check(mw_dycore_get_background(handle, hyc.data(), hytc.data(), hye.data(), hyte.data()), "mw_dycore_get_background");
     dm.get<real, 2>("hy_dens_cells").copy_from_host(hyc.data());
     dm.get<real, 2>("hy_dens_theta_cells").copy_from_host(hytc.data());
+    if (out_freq >= 0.) { yakl::fence(); output(coupler, etime); }  // DYC:1659: the initial state
     // DYC:1671-1676 register state_flux_{x,y,z} / tracers_flux_{x,y,z}: no reader exists in the reference outside the
     // dycore itself, and the fused stage kernel never materialises the state fluxes, so they are not
     // allocated here (3N fields of HBM saved).
+  }
+
+  // DYC:2019-2191: append the coupler fields to <out_prefix>.nc (one shared file; every rank writes its own block) or
+  // <out_prefix>_<rank>.nc (file_per_process) as record variables (t,z,y,x) next to x, y, z, t -- NetCDF classic format
+  // written directly (mw_netcdf.h), since neither NetCDF-C nor PNetCDF exists on this image.  iens = 0 like the reference.
+  void output(core::Coupler const &coupler, real etime) const {
+    yakl::timer_start("output");
+    bool const per_proc = coupler.get_option<bool>("file_per_process", false);
+    size_t const nx = coupler.get_nx(), ny = coupler.get_ny(), nz = coupler.get_nz();
+    size_t const i_beg = coupler.get_i_beg(), j_beg = coupler.get_j_beg();
+    std::stringstream fname;
+    fname << coupler.get_option<std::string>("out_prefix");
+    if (per_proc) fname << "_" << std::setw(8) << std::setfill('0') << coupler.get_myrank();
+    fname << ".nc";
+    std::vector<std::string> varnames = {"density_dry", "uvel", "vvel", "wvel", "temp"};
+    for (auto &t : coupler.get_tracer_names()) varnames.push_back(t);
+    bool const writer0 = per_proc || coupler.is_mainproc();
+    try {
+      mw::NetCDFWriter nc(fname.str(), per_proc ? nx : coupler.get_nx_glob(), per_proc ? ny : coupler.get_ny_glob(), nz, varnames);
+      size_t rec = 0;
+      if (etime == 0) {
+        if (writer0) nc.create(coupler.get_dx(), coupler.get_dy(), coupler.get_dz(), per_proc ? i_beg : 0, per_proc ? j_beg : 0);
+      }
+      mw::check(mw_comm_barrier(coupler.get_comm()), "mw_comm_barrier");
+      if (etime != 0) rec = mw::NetCDFWriter::num_records(fname.str());
+      mw::check(mw_comm_barrier(coupler.get_comm()), "mw_comm_barrier");
+      if (writer0) nc.write_time(rec, etime);
+      auto &dm = coupler.get_data_manager_readonly();
+      for (size_t f = 0; f < varnames.size(); ++f) {
+        auto h = dm.get<real const, 4>(varnames[f]).createHostCopy();
+        nc.write_block(rec, f, h.data(), ny, nx, per_proc ? 0 : j_beg, per_proc ? 0 : i_beg);
+      }
+      mw::check(mw_comm_barrier(coupler.get_comm()), "mw_comm_barrier");
+    } catch (std::runtime_error const &e) { endrun(e.what()); }
+    yakl::timer_stop("output");
   }
 
   // refresh the immersed-boundary switch after another module changed "immersed_proportion" / the option

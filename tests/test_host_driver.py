@@ -178,3 +178,33 @@ def test_host_driver_surrogate_reads_keras_h5(tmp_path, golden):
     bad.write_text(base + "\nkeras_weights_h5: %s\n" % (tmp_path / "in.txt"))
     r = subprocess.run([exe, str(bad), "steps=1", "quiet=1", "surrogate=1"], capture_output=True, text=True)
     assert r.returncode != 0 and "not an HDF5 file" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("per_proc", [False, True])
+def test_host_driver_writes_netcdf_output(tmp_path, golden, per_proc):
+    """dycore.output (DYC:2019-2191) through the host module: the initial state plus one record every out_freq seconds, in the
+    reference's file layout (dims x,y,z,t; variables x,y,z,t and (t,z,y,x) fields), readable by a stock NetCDF reader"""
+    from scipy.io import netcdf_file
+    build_driver()
+    exe = os.path.join(HOST, "driver")
+    g = golden("config1_full10.npz")
+    base = open(os.path.join(GOLD, "input_config1.yaml")).read().replace("out_freq: 100.", "out_freq: 2.0")
+    y = tmp_path / "in.yaml"
+    y.write_text(base + "\nfile_per_process: %s\n" % ("true" if per_proc else "false"))
+    r = subprocess.run([exe, str(y), "steps=10", "dump=" + str(tmp_path / "s.bin")], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert r.stdout.count("Etime , dtphys, maxw:") == 3                       # the reference's progress line (DYC:189-195)
+    fn = tmp_path / ("test_00000000.nc" if per_proc else "test.nc")
+    with netcdf_file(str(fn), "r", mmap=False) as nc:
+        assert list(nc.variables)[:9] == ["x", "y", "z", "t", "density_dry", "uvel", "vvel", "wvel", "temp"]
+        assert list(nc.variables)[9:] == ["water_vapor", "cloud_liquid", "precip_liquid"]
+        t = nc.variables["t"][:]
+        dt = float(g["dt"])
+        assert len(t) == 4 and t[0] == 0 and np.allclose(t[1:], [3 * dt, 6 * dt, 9 * dt])
+        assert np.allclose(nc.variables["x"][:], (np.arange(100) + 0.5) * 1000.0)
+        assert np.allclose(nc.variables["z"][:], (np.arange(40) + 0.5) * 500.0)
+        rho0 = nc.variables["density_dry"][0]
+        assert rho0.shape == (40, 1, 100)
+        assert np.abs(rho0 - g["s0"][0]).max() <= 1e-13 * np.abs(g["s0"][0]).max()      # record 0 = the initial state
+        assert np.abs(nc.variables["uvel"][3]).max() > 1.0 and np.isfinite(nc.variables["temp"][3]).all()
