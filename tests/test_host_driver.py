@@ -181,8 +181,7 @@ def test_host_driver_surrogate_reads_keras_h5(tmp_path, golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("per_proc", [False, True])
-def test_host_driver_writes_netcdf_output(tmp_path, golden, per_proc):
+def test_host_driver_writes_netcdf_output(tmp_path, golden):
     """dycore.output (DYC:2019-2191) through the host module: the initial state plus one record every out_freq seconds, in the
     reference's file layout (dims x,y,z,t; variables x,y,z,t and (t,z,y,x) fields), readable by a stock NetCDF reader"""
     from scipy.io import netcdf_file
@@ -191,12 +190,11 @@ def test_host_driver_writes_netcdf_output(tmp_path, golden, per_proc):
     g = golden("config1_full10.npz")
     base = open(os.path.join(GOLD, "input_config1.yaml")).read().replace("out_freq: 100.", "out_freq: 2.0")
     y = tmp_path / "in.yaml"
-    y.write_text(base + "\nfile_per_process: %s\n" % ("true" if per_proc else "false"))
+    y.write_text(base)
     r = subprocess.run([exe, str(y), "steps=10", "dump=" + str(tmp_path / "s.bin")], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     assert r.stdout.count("Etime , dtphys, maxw:") == 3                       # the reference's progress line (DYC:189-195)
-    fn = tmp_path / ("test_00000000.nc" if per_proc else "test.nc")
-    with netcdf_file(str(fn), "r", mmap=False) as nc:
+    with netcdf_file(str(tmp_path / "test.nc"), "r", mmap=False) as nc:
         assert list(nc.variables)[:9] == ["x", "y", "z", "t", "density_dry", "uvel", "vvel", "wvel", "temp"]
         assert list(nc.variables)[9:] == ["water_vapor", "cloud_liquid", "precip_liquid"]
         t = nc.variables["t"][:]
@@ -208,3 +206,25 @@ def test_host_driver_writes_netcdf_output(tmp_path, golden, per_proc):
         assert rho0.shape == (40, 1, 100)
         assert np.abs(rho0 - g["s0"][0]).max() <= 1e-13 * np.abs(g["s0"][0]).max()      # record 0 = the initial state
         assert np.abs(nc.variables["uvel"][3]).max() > 1.0 and np.isfinite(nc.variables["temp"][3]).all()
+
+
+@pytest.mark.gpu
+def test_host_city_driver_writes_file_per_process(tmp_path, golden):
+    """file_per_process: true (experiments/simple_city/driver.cpp:37) -> <out_prefix>_<rank>.nc (DYC:2036-2101)"""
+    from scipy.io import netcdf_file
+    build_driver()
+    exe = os.path.join(HOST, "driver_city")
+    g = golden("building_city_loop6.npz")
+    base = open(os.path.join(GOLD, "input_building.yaml")).read()
+    y = tmp_path / "in.yaml"
+    y.write_text(base.replace("out_freq: 10.", "out_freq: 0.05").replace("file_per_process: false", "file_per_process: true"))
+    r = subprocess.run([exe, str(y), "steps=6", "dump=" + str(tmp_path / "s.bin")], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    with netcdf_file(str(tmp_path / "test_00000000.nc"), "r", mmap=False) as nc:
+        assert list(nc.variables) == ["x", "y", "z", "t", "density_dry", "uvel", "vvel", "wvel", "temp", "water_vapor"]
+        assert len(nc.variables["t"][:]) == 4
+        u0 = nc.variables["uvel"][0]
+        assert u0.shape == (12, 30, 40) and np.abs(u0 - g["s0"][1]).max() <= 1e-13 * 20
+    raw = np.fromfile(tmp_path / "s.bin").reshape(13, 12, 30, 40)
+    _compare(raw[:6], g["s1"])                                             # output on the way does not disturb the run
+    assert os.path.exists(tmp_path / "time_averaged_fields.0.bin")
