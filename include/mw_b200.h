@@ -186,6 +186,14 @@ int  mw_horizontal_sponge_apply(int nfields, double *const *fields, const double
 int  mw_time_average_accumulate(int nfields, double *const *avg, const double *const *val, long long n, double etime,
                                 double dt, void *stream);
 
+/* ---- ensemble members ------------------------------------------------------------------------------------------ */
+/* The reference's fields are [nz][ny][nx][nens] (CPL:328); the kernels here take one member [nz][ny][nx].  gather copies
+ * member iens of each interleaved field into a contiguous member array, scatter writes it back (ncell = nz*ny*nx). */
+int  mw_ensemble_gather(int nfields, double *const *member, const double *const *fields, long long ncell, int nens,
+                        int iens, void *stream);
+int  mw_ensemble_scatter(int nfields, double *const *fields, const double *const *member, long long ncell, int nens,
+                         int iens, void *stream);
+
 /* ---- communicator (NCCL over NVLink), one process per GPU -------------------------------------------------- */
 int  mw_comm_unique_id(void *id_bytes_128);                       /* rank 0 creates, caller broadcasts            */
 int  mw_comm_create(const void *id_bytes_128, int nranks, int rank, mw_comm **out);

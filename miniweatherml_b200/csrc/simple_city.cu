@@ -128,3 +128,51 @@ extern "C" int mw_time_average_accumulate(int nfields, double *const *avg, const
   MW_CUDA_OK(cudaGetLastError());
   return MW_OK;
 }
+
+// ---- ensemble members (nens > 1) ------------------------------------------------------------------------------------
+// The reference keeps the ensemble index innermost, fields are [nz][ny][nx][nens] (CPL:328); every kernel of this library
+// works on one member laid out [nz][ny][nx].  The host modules therefore stage member by member: gather member e into
+// contiguous scratch fields, run the member, scatter back.  Both are plain strided streams.
+namespace mw {
+namespace {
+struct EnsParams {
+  double *dst[MAXF];
+  const double *src[MAXF];
+  int nf, nens, iens;
+  long long ncell;
+};
+template <bool GATHER>
+__global__ void __launch_bounds__(256) k_ensemble_copy(const EnsParams P) {
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x; c < P.ncell; c += stride)
+    for (int f = 0; f < P.nf; ++f) {
+      if (GATHER) P.dst[f][c] = __ldg(P.src[f] + c * P.nens + P.iens);
+      else P.dst[f][c * P.nens + P.iens] = __ldg(P.src[f] + c);
+    }
+}
+int ensemble_copy(bool gather, int nf, double *const *dst, const double *const *src, long long ncell, int nens, int iens, void *stream) {
+  int rc = device_check_cached();
+  if (rc != MW_OK) return rc;
+  MW_REQUIRE(dst && src && nf >= 1 && nf <= MAXF && ncell >= 0 && nens >= 1 && iens >= 0 && iens < nens, "mw_ensemble_%s: bad argument",
+             gather ? "gather" : "scatter");
+  if (ncell == 0) return MW_OK;
+  EnsParams P;
+  P.nf = nf; P.nens = nens; P.iens = iens; P.ncell = ncell;
+  for (int f = 0; f < nf; ++f) { P.dst[f] = dst[f]; P.src[f] = src[f]; }
+  const int grid = (int) std::min<long long>((ncell + 255) / 256, 148 * 16);
+  if (gather) k_ensemble_copy<true><<<grid, 256, 0, (cudaStream_t) stream>>>(P);
+  else k_ensemble_copy<false><<<grid, 256, 0, (cudaStream_t) stream>>>(P);
+  MW_CUDA_OK(cudaGetLastError());
+  return MW_OK;
+}
+}  // namespace
+}  // namespace mw
+
+extern "C" int mw_ensemble_gather(int nfields, double *const *member, const double *const *fields, long long ncell, int nens,
+                                  int iens, void *stream) {
+  return ensemble_copy(true, nfields, member, fields, ncell, nens, iens, stream);
+}
+extern "C" int mw_ensemble_scatter(int nfields, double *const *fields, const double *const *member, long long ncell, int nens,
+                                   int iens, void *stream) {
+  return ensemble_copy(false, nfields, fields, member, ncell, nens, iens, stream);
+}

@@ -2,27 +2,34 @@
 // (density_dry, uvel, vvel, temp, water_vapor) to the initial profile with a 900 s time scale.
 #pragma once
 #include "coupler.h"
+#include "ensemble.h"
 
 namespace modules {
 class ColumnNudger {
  public:
   int static constexpr num_fields = 5;
-  double *column = nullptr;                                         // device [5][nz]
+  double *column = nullptr;                                         // device [nens][5][nz]
 
   ~ColumnNudger() { if (column) mw_free(column); }
 
   void set_column(core::Coupler &coupler) {                         // column_nudging.h:15-36
     auto ptrs = state_pointers(coupler);
-    if (!column) mw::check(mw_malloc((void **) &column, (size_t) num_fields * coupler.get_nz() * sizeof(double)), "mw_malloc");
-    mw::check(mw_column_average(ptrs.data(), coupler.get_nz(), coupler.get_ny(), coupler.get_nx(), nglob(coupler), column,
-                                coupler.get_comm(), nullptr), "mw_column_average");
+    size_t const per = (size_t) num_fields * coupler.get_nz();
+    if (!column) mw::check(mw_malloc((void **) &column, per * coupler.get_nens() * sizeof(double)), "mw_malloc");
+    mw::for_each_member(ptrs, mw::member_cells(coupler), coupler.get_nens(), false, [&](std::vector<double *> const &member, int iens) {
+      mw::check(mw_column_average(member.data(), coupler.get_nz(), coupler.get_ny(), coupler.get_nx(), nglob(coupler), column + per * iens,
+                                  coupler.get_comm(), nullptr), "mw_column_average");
+    });
   }
 
   void nudge_to_column(core::Coupler &coupler, real dt) {           // column_nudging.h:39-67
     if (!column) endrun("ERROR: ColumnNudger::nudge_to_column called before set_column");
     auto ptrs = state_pointers(coupler);
-    mw::check(mw_nudge_to_column(const_cast<double *const *>(ptrs.data()), coupler.get_nz(), coupler.get_ny(), coupler.get_nx(),
-                                 nglob(coupler), dt, column, coupler.get_comm(), nullptr), "mw_nudge_to_column");
+    size_t const per = (size_t) num_fields * coupler.get_nz();
+    mw::for_each_member(ptrs, mw::member_cells(coupler), coupler.get_nens(), true, [&](std::vector<double *> const &member, int iens) {
+      mw::check(mw_nudge_to_column(member.data(), coupler.get_nz(), coupler.get_ny(), coupler.get_nx(), nglob(coupler), dt,
+                                   column + per * iens, coupler.get_comm(), nullptr), "mw_nudge_to_column");
+    });
   }
 
  private:

@@ -47,7 +47,7 @@ class Coupler {
                                                  int i_beg_in = -1, int i_end_in = -1, int j_beg_in = -1, int j_end_in = -1) {
     auto &rt = mw::Runtime::get();
     rt.init();
-    if (nens != 1) endrun("ERROR: nens = " + std::to_string(nens) + ": the B200 path implements nens == 1 only");
+    if (nens < 1) endrun("ERROR: nens = " + std::to_string(nens));      // members are staged one at a time, see ensemble.h
     this->nens = nens; this->nx_glob = nx_glob; this->ny_glob = ny_glob;
     nranks = rt.nranks; myrank = rt.rank; mainproc = (myrank == 0);
     bool sim2d = ny_glob == 1;

@@ -1,8 +1,9 @@
 // The reference's canonical driver (experiments/supercell_example/driver.cpp:1-90) against the B200 modules: the
 // statements between the two marker comments below are the reference's, unchanged in order and meaning; only the
 // include directory differs (-I miniweatherml_b200/host instead of -I model/...).  Additions for testing are
-// confined to the optional extra arguments:  driver input.yaml [steps=N] [dump=state.bin] [surrogate=1] [quiet=1]
+// confined to the optional extra arguments:  driver input.yaml [steps=N] [dump=state.bin] [load=state.bin] [surrogate=1] [quiet=1]
 //   steps=N    stop after N physics steps (parity runs)      dump=FILE  raw fp64 dump of the coupler fields at the end
+//   load=FILE  replace the initial coupler fields (same raw layout as dump, [field][nz][ny][nx][nens]) after init
 #include "coupler.h"
 #include "dynamics_euler_stratified_wenofv.h"
 #include "microphysics_kessler.h"
@@ -45,6 +46,20 @@ template <class MICRO> static int run(int argc, char **argv, std::map<std::strin
   dycore.init(coupler);
   column_nudger.set_column(coupler);
   modules::perturb_temperature(coupler);
+
+  if (extra.count("load")) {                                          // single rank: the whole state from one file
+    auto &dm = coupler.get_data_manager_readwrite();
+    std::ifstream f(extra.at("load"), std::ios::binary);
+    if (!f) endrun("ERROR: cannot open " + extra.at("load"));
+    std::vector<std::string> names = {"density_dry", "uvel", "vvel", "wvel", "temp"};
+    for (auto &t : coupler.get_tracer_names()) names.push_back(t);
+    for (auto &nm : names) {
+      auto v = dm.get<real, 4>(nm);
+      std::vector<real> h(v.size());
+      if (!f.read((char *) h.data(), h.size() * sizeof(real))) endrun("ERROR: " + extra.at("load") + " is too short");
+      v.copy_from_host(h.data());
+    }
+  }
 
   long max_steps = extra.count("steps") ? atol(extra.at("steps").c_str()) : -1, nstep = 0;
   real etime = 0;

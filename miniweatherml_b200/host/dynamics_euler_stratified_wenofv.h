@@ -4,6 +4,7 @@
 // BASELINE.json calls this class "Dynamics_Euler_Stateless"; an alias is provided below.
 #pragma once
 #include "coupler.h"
+#include "ensemble.h"
 #include "mw_netcdf.h"
 #include <iomanip>
 #include <random>
@@ -24,11 +25,12 @@ class Dynamics_Euler_Stratified_WenoFV {
   real etime = 0, out_freq = -1;
   int num_out = 0;
   int idWV = -1;
-  std::vector<double *> field_ptrs;
+  std::vector<double *> field_ptrs;                                // coupler fields, [nz][ny][nx][nens]
+  double *imm_member = nullptr;                                     // nens > 1: the current member's immersed_proportion
 
  public:
   Dynamics_Euler_Stratified_WenoFV() { memset(&cfg, 0, sizeof(cfg)); }
-  ~Dynamics_Euler_Stratified_WenoFV() { if (handle) mw_dycore_destroy(handle); }
+  ~Dynamics_Euler_Stratified_WenoFV() { if (handle) mw_dycore_destroy(handle); if (imm_member) mw_free(imm_member); }
   Dynamics_Euler_Stratified_WenoFV(Dynamics_Euler_Stratified_WenoFV const &) = delete;
   Dynamics_Euler_Stratified_WenoFV &operator=(Dynamics_Euler_Stratified_WenoFV const &) = delete;
 
@@ -42,7 +44,18 @@ class Dynamics_Euler_Stratified_WenoFV {
   // DYC:81-198: SSPRK3 with sub-cycling; state converted from / to the coupler's (rho_d,u,v,w,T,tracer densities)
   void time_step(core::Coupler &coupler, real &dt_phys) {
     if (!handle) endrun("ERROR: Dynamics_Euler_Stratified_WenoFV::time_step called before init");
-    mw::check(mw_dycore_time_step(handle, field_ptrs.data(), dt_phys, nullptr), "mw_dycore_time_step");
+    int const nens = coupler.get_nens();
+    size_t const ncell = mw::member_cells(coupler);
+    real const dt_in = dt_phys;
+    bool const immersed = nens > 1 && coupler.get_option<bool>("use_immersed_boundaries", false);
+    mw::for_each_member(field_ptrs, ncell, nens, true, [&](std::vector<double *> const &member, int iens) {   // DYC: every kernel loops iens
+      if (immersed) {
+        double *imm[1] = {imm_member};
+        double const *src[1] = {coupler.get_data_manager_readonly().get<real const, 4>("immersed_proportion").data()};
+        mw::check(mw_ensemble_gather(1, imm, src, (long long) ncell, nens, iens, nullptr), "mw_ensemble_gather");
+      }
+      mw::check(mw_dycore_time_step(handle, member.data(), dt_in, nullptr), "mw_dycore_time_step");
+    });
     etime += dt_phys;
     if (out_freq >= 0. && etime / out_freq >= num_out + 1) {        // DYC:184-196
       yakl::fence();
@@ -110,7 +123,7 @@ class Dynamics_Euler_Stratified_WenoFV {
 
     etime = 0; num_out = 0;
 
-    cfg.nx = nx; cfg.ny = ny; cfg.nz = nz; cfg.nens = nens;
+    cfg.nx = nx; cfg.ny = ny; cfg.nz = nz; cfg.nens = 1;              // the handle works on one member at a time (ensemble.h)
     cfg.nx_glob = (int) coupler.get_nx_glob(); cfg.ny_glob = (int) coupler.get_ny_glob();
     cfg.i_beg = (int) coupler.get_i_beg(); cfg.j_beg = (int) coupler.get_j_beg();
     cfg.nproc_x = coupler.get_nproc_x(); cfg.nproc_y = coupler.get_nproc_y(); cfg.px = coupler.get_px(); cfg.py = coupler.get_py();
@@ -135,15 +148,25 @@ class Dynamics_Euler_Stratified_WenoFV {
     field_ptrs.clear();
     for (auto nm : {"density_dry", "uvel", "vvel", "wvel", "temp"}) field_ptrs.push_back(dm.get<real, 4>(nm).data());
     for (auto &nm : tracer_names) field_ptrs.push_back(dm.get<real, 4>(nm).data());
-    // the test case's state + convert_dynamics_to_coupler (DYC:1656), and for building / city the immersed mask
+    // the test case's state + convert_dynamics_to_coupler (DYC:1656), and for building / city the immersed mask; every
+    // ensemble member gets the same state (the reference's initialisers ignore iens)
+    size_t const ncell = mw::member_cells(coupler);
+    std::vector<double *> init_ptrs = field_ptrs;
+    double *imm_ptr = dm.get<real, 4>("immersed_proportion").data();
+    if (nens > 1) {
+      init_ptrs = mw::member_scratch().get(field_ptrs.size(), ncell);
+      if (imm_member) mw_free(imm_member);
+      mw::check(mw_malloc((void **) &imm_member, ncell * sizeof(double)), "mw_malloc");
+      mw::check(mw_memset(imm_member, 0, ncell * sizeof(double), nullptr), "mw_memset");
+      imm_ptr = imm_member;
+    }
     if (init_data == "supercell") {                                 // DYC:1687-1887
-      mw::check(mw_dycore_init_supercell(handle, field_ptrs.data(), nullptr), "mw_dycore_init_supercell");
+      mw::check(mw_dycore_init_supercell(handle, init_ptrs.data(), nullptr), "mw_dycore_init_supercell");
     } else if (init_data == "thermal") {                            // DYC:1338-1419
-      mw::check(mw_dycore_init_thermal(handle, field_ptrs.data(), nullptr), "mw_dycore_init_thermal");
+      mw::check(mw_dycore_init_thermal(handle, init_ptrs.data(), nullptr), "mw_dycore_init_thermal");
     } else if (init_data == "building") {                           // DYC:1544-1651
       coupler.set_option<bool>("use_immersed_boundaries", true);
-      mw::check(mw_dycore_init_building(handle, field_ptrs.data(), dm.get<real, 4>("immersed_proportion").data(), nullptr),
-                "mw_dycore_init_building");
+      mw::check(mw_dycore_init_building(handle, init_ptrs.data(), imm_ptr, nullptr), "mw_dycore_init_building");
     } else {                                                        // city, DYC:1421-1542
       coupler.set_option<bool>("use_immersed_boundaries", true);
       int cells_per_building = 0, nbuildings_y = 0, nbuildings_x = 0;
@@ -154,8 +177,16 @@ class Dynamics_Euler_Stratified_WenoFV {
       std::mt19937 gen{17};
       std::normal_distribution<> d{60, 10};
       for (auto &hgt : building_heights) hgt = d(gen);
-      mw::check(mw_dycore_init_city(handle, field_ptrs.data(), dm.get<real, 4>("immersed_proportion").data(),
-                                    building_heights.data(), nbuildings_y, nbuildings_x, nullptr), "mw_dycore_init_city");
+      mw::check(mw_dycore_init_city(handle, init_ptrs.data(), imm_ptr, building_heights.data(), nbuildings_y, nbuildings_x, nullptr),
+                "mw_dycore_init_city");
+    }
+    if (nens > 1) {
+      double *imm_all[1] = {dm.get<real, 4>("immersed_proportion").data()};
+      double const *imm_src[1] = {imm_member};
+      for (int e = 0; e < nens; ++e) {
+        mw::check(mw_ensemble_scatter((int) field_ptrs.size(), field_ptrs.data(), init_ptrs.data(), (long long) ncell, nens, e, nullptr), "mw_ensemble_scatter");
+        mw::check(mw_ensemble_scatter(1, imm_all, imm_src, (long long) ncell, nens, e, nullptr), "mw_ensemble_scatter");
+      }
     }
 
     // DYC:1663-1668: background profiles visible to other modules
@@ -163,8 +194,10 @@ class Dynamics_Euler_Stratified_WenoFV {
     dm.register_and_allocate<real>("hy_dens_theta_cells", "hydrostatic density*theta cell averages", {nz, nens});
     std::vector<double> hyc(nz), hytc(nz), hye(nz + 1), hyte(nz + 1);
     mw::check(mw_dycore_get_background(handle, hyc.data(), hytc.data(), hye.data(), hyte.data()), "mw_dycore_get_background");
-    dm.get<real, 2>("hy_dens_cells").copy_from_host(hyc.data());
-    dm.get<real, 2>("hy_dens_theta_cells").copy_from_host(hytc.data());
+    std::vector<double> hyc_e((size_t) nz * nens), hytc_e((size_t) nz * nens);      // {nz,nens}: same profile for every member
+    for (int k = 0; k < nz; ++k) for (int e = 0; e < nens; ++e) { hyc_e[(size_t) k * nens + e] = hyc[k]; hytc_e[(size_t) k * nens + e] = hytc[k]; }
+    dm.get<real, 2>("hy_dens_cells").copy_from_host(hyc_e.data());
+    dm.get<real, 2>("hy_dens_theta_cells").copy_from_host(hytc_e.data());
     if (out_freq >= 0.) { yakl::fence(); output(coupler, etime); }  // DYC:1659: the initial state
     // DYC:1671-1676 register state_flux_{x,y,z} / tracers_flux_{x,y,z}: no reader exists in the reference outside the
     // dycore itself, and the fused stage kernel never materialises the state fluxes, so they are not
@@ -199,6 +232,8 @@ class Dynamics_Euler_Stratified_WenoFV {
       auto &dm = coupler.get_data_manager_readonly();
       for (size_t f = 0; f < varnames.size(); ++f) {
         auto h = dm.get<real const, 4>(varnames[f]).createHostCopy();
+        int const nens = coupler.get_nens();
+        if (nens > 1) { for (size_t c = 0; c < nz * ny * nx; ++c) h[c] = h[c * nens]; }      // iens = 0 (DYC:2033)
         nc.write_block(rec, f, h.data(), ny, nx, per_proc ? 0 : j_beg, per_proc ? 0 : i_beg);
       }
       mw::check(mw_comm_barrier(coupler.get_comm()), "mw_comm_barrier");
@@ -210,7 +245,12 @@ class Dynamics_Euler_Stratified_WenoFV {
   void update_immersed(core::Coupler &coupler) {
     bool use = coupler.get_option<bool>("use_immersed_boundaries", false);
     auto &dm = coupler.get_data_manager_readwrite();
-    mw::check(mw_dycore_set_immersed(handle, use ? dm.get<real, 4>("immersed_proportion").data() : nullptr), "mw_dycore_set_immersed");
+    double const *mask = dm.get<real, 4>("immersed_proportion").data();
+    if (coupler.get_nens() > 1) {                                    // members are staged through imm_member (time_step)
+      if (!imm_member) mw::check(mw_malloc((void **) &imm_member, mw::member_cells(coupler) * sizeof(double)), "mw_malloc");
+      mask = imm_member;
+    }
+    mw::check(mw_dycore_set_immersed(handle, use ? mask : nullptr), "mw_dycore_set_immersed");
   }
 
   mw_dycore *get_handle() const { return handle; }

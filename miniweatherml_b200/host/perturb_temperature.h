@@ -2,6 +2,7 @@
 // default the drivers use) runs on the device; the PRNG variant is not on the benchmarked path and is rejected.
 #pragma once
 #include "coupler.h"
+#include "ensemble.h"
 
 namespace modules {
 inline void perturb_temperature(core::Coupler &coupler, bool thermal = true, bool random = false) {
@@ -9,8 +10,10 @@ inline void perturb_temperature(core::Coupler &coupler, bool thermal = true, boo
   if (!thermal) return;
   auto &dm = coupler.get_data_manager_readwrite();
   auto temp = dm.get<real, 4>("temp");
-  mw::check(mw_perturb_temperature(temp.data(), coupler.get_nz(), coupler.get_ny(), coupler.get_nx(), (int) coupler.get_i_beg(),
-                                   (int) coupler.get_j_beg(), coupler.get_dx(), coupler.get_dy(), coupler.get_dz(),
-                                   coupler.get_xlen(), coupler.get_ylen(), nullptr), "mw_perturb_temperature");
+  mw::for_each_member({temp.data()}, mw::member_cells(coupler), coupler.get_nens(), true, [&](std::vector<double *> const &member, int) {
+    mw::check(mw_perturb_temperature(member[0], coupler.get_nz(), coupler.get_ny(), coupler.get_nx(), (int) coupler.get_i_beg(),
+                                     (int) coupler.get_j_beg(), coupler.get_dx(), coupler.get_dy(), coupler.get_dz(),
+                                     coupler.get_xlen(), coupler.get_ylen(), nullptr), "mw_perturb_temperature");
+  });
 }
 }  // namespace modules

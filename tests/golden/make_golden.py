@@ -94,8 +94,42 @@ def keras_weight_fixtures(tmp):
                         scl_out=np.loadtxt(ex + "supercell_kessler_stencil_output_scaling.txt"))
 
 
+def ensemble_fixtures(tmp):
+    """nens = 2 (fields [nz][ny][nx][nens], CPL:328): two DIFFERENT members through the full step loop, and the shipped
+    city configuration's two identical members through the simple_city loop."""
+    g = dict(nx=20, ny=12, nz=12, xlen=20e3, ylen=12e3, zlen=12e3)
+    shp = (8, g["nz"], g["ny"], g["nx"], 2)
+    O.ref_run(tmp, steps=0, tracers="kessler", nens=2, out0=tmp + "/e0.bin", **g)
+    s0 = np.fromfile(tmp + "/e0.bin").reshape(shp)
+    k = np.arange(g["nz"])[:, None, None]
+    j = np.arange(g["ny"])[None, :, None]
+    i = np.arange(g["nx"])[None, None, :]
+    bump = np.sin(2 * np.pi * i / g["nx"]) * np.cos(2 * np.pi * j / g["ny"]) * np.sin(np.pi * (k + 0.5) / g["nz"])
+    s0[1, ..., 1] = 0.5 * s0[1, ..., 1] + 2.0 * bump          # member 1: weaker shear plus a wave, warmer, moister low levels
+    s0[2, ..., 1] = 1.5 * bump
+    s0[4, ..., 1] += 0.8 * bump
+    s0[5, ..., 1] *= 1.0 + 0.2 * bump
+    s0 = np.ascontiguousarray(s0)
+    s0.tofile(tmp + "/e0m.bin")
+    r = O.ref_run(tmp, steps=3, tracers="kessler", nens=2, micro=1, sponge=1, nudge=1, perturb=0, out=tmp + "/e1.bin",
+                  **{"in": tmp + "/e0m.bin"}, **g)
+    s1 = np.fromfile(tmp + "/e1.bin").reshape(shp)
+    assert np.abs(s1[..., 0] - s1[..., 1]).max() > 0.1
+    np.savez_compressed(HERE + "/box3d_nens2_full3.npz", s0=s0, s1=s1, dt=r[-1]["dt"], steps=3, **g)
+    g = dict(nx=50, ny=50, nz=12, xlen=1500., ylen=1500., zlen=120.)
+    r = O.ref_run(tmp, steps=3, tracers="vapor", nens=2, perturb=0, init_data="city", enable_gravity=1, hsponge=1, sponge=1,
+                  sponge_ts=1, out=tmp + "/c1.bin", imm=tmp + "/ci.bin", **g)
+    s1 = np.fromfile(tmp + "/c1.bin").reshape(6, g["nz"], g["ny"], g["nx"], 2)
+    imm = np.fromfile(tmp + "/ci.bin").reshape(g["nz"], g["ny"], g["nx"], 2)
+    np.savez_compressed(HERE + "/city_nens2_loop3.npz", s1=s1[..., :1].copy(), members_identical=bool(np.array_equal(s1[..., 0], s1[..., 1])),
+                        imm=imm[..., 0].copy(), dt=r[-1]["dt"], steps=3, **g)
+
+
 def main():
     tmp = tempfile.mkdtemp()
+    if "--ensemble" in sys.argv:
+        ensemble_fixtures(tmp)
+        return
     if "--config4" in sys.argv:
         config4_and_thermal(tmp)
         return
@@ -175,6 +209,7 @@ def main():
     np.savez_compressed(HERE + "/ponni_mlp_kat.npz", w=w, x=x, y=y)
     config4_and_thermal(tmp)
     keras_weight_fixtures(tmp)
+    ensemble_fixtures(tmp)
     print("golden fixtures written to", HERE)
 
 

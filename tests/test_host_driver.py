@@ -228,3 +228,41 @@ def test_host_city_driver_writes_file_per_process(tmp_path, golden):
     raw = np.fromfile(tmp_path / "s.bin").reshape(13, 12, 30, 40)
     _compare(raw[:6], g["s1"])                                             # output on the way does not disturb the run
     assert os.path.exists(tmp_path / "time_averaged_fields.0.bin")
+
+
+@pytest.mark.gpu
+def test_host_driver_two_different_ensemble_members(tmp_path, golden):
+    """nens = 2, fields [nz][ny][nx][nens] (CPL:328): two different members through dycore + Kessler + sponge + nudging;
+    the host modules stage member by member (host/ensemble.h), Kessler and its global rainsplit see all columns at once"""
+    build_driver()
+    exe = os.path.join(HOST, "driver")
+    g = golden("box3d_nens2_full3.npz")
+    y = tmp_path / "in.yaml"
+    y.write_text(open(os.path.join(GOLD, "input_box3d.yaml")).read().replace("nens   : 1", "nens   : 2"))
+    g["s0"].tofile(tmp_path / "s0.bin")
+    r = subprocess.run([exe, str(y), "steps=%d" % int(g["steps"]), "load=" + str(tmp_path / "s0.bin"), "dump=" + str(tmp_path / "s1.bin"),
+                        "quiet=1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = np.fromfile(tmp_path / "s1.bin")[:g["s1"].size].reshape(g["s1"].shape)
+    assert np.abs(out[..., 0] - out[..., 1]).max() > 0.1                        # the members really differ
+    _compare(out, g["s1"])
+    for e in range(2):
+        _compare(out[..., e], g["s1"][..., e])
+
+
+@pytest.mark.gpu
+def test_host_city_driver_shipped_ensemble_of_two(tmp_path, golden):
+    """the shipped input_city.yaml asks for nens = 2 (experiments/simple_city/inputs/input_city.yaml:6): init, immersed
+    mask, Horizontal_Sponge, dycore and sponge_layer for both members against the compiled reference"""
+    build_driver()
+    exe = os.path.join(HOST, "driver_city")
+    g = golden("city_nens2_loop3.npz")
+    assert bool(g["members_identical"])
+    y = tmp_path / "in.yaml"
+    y.write_text(open(os.path.join(GOLD, "input_city.yaml")).read().replace("nens   : 1", "nens   : 2"))
+    dump, meta = _run(exe, str(y), int(g["steps"]), str(tmp_path))
+    nz, ny, nx = g["imm"].shape
+    raw = np.fromfile(dump).reshape(13, nz, ny, nx, 2)
+    for e in range(2):
+        _compare(raw[:6, ..., e], g["s1"][..., 0])
+        assert np.array_equal(raw[6, ..., e], g["imm"])
