@@ -91,6 +91,7 @@ static int tile_variant(int nt) {
     const char *t = getenv("MW_NO_TMA");
     if (t && atoi(t) != 0) v = 0;                           // the plain-load path exists in the phase kernel only
   }
+  if (v == 4) return nt <= 3 ? 4 : 0;                    // ws kernel with segment reconstructions
   if (v == 3) return nt <= 1 ? 3 : (nt <= 3 ? 2 : 0);    // uniform-jobs kernel (stage_uj.cuh) where it fits in smem
   if (v == 2) return nt <= 3 ? 2 : 0;
   return (nt <= 1) ? v : 0;
@@ -478,6 +479,11 @@ template <int NT> struct WsKernel<NT, 2> {
   static void launch(dim3 g, cudaStream_t st, const CUtensorMap &m, const StageParams &P) { k_stage_ws<NT, 16, 8><<<g, C::NTHR, C::SMEM, st>>>(m, P); }
   static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_ws<NT, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
 };
+template <int NT> struct WsKernel<NT, 4> {                       // ws kernel with segment reconstructions (SEG = true)
+  using C = WsCfg<NT, 16, 8>;
+  static void launch(dim3 g, cudaStream_t st, const CUtensorMap &m, const StageParams &P) { k_stage_ws<NT, 16, 8, true><<<g, C::NTHR, C::SMEM, st>>>(m, P); }
+  static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_ws<NT, 16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
+};
 template <int NT> struct WsKernel<NT, 3> {
   using C = UjCfg<NT, 16, 8>;
   static void launch(dim3 g, cudaStream_t st, const CUtensorMap &m, const StageParams &P) { k_stage_uj<NT, 16, 8><<<g, C::NTHR, C::SMEM, st>>>(m, P); }
@@ -535,6 +541,7 @@ static int launch_stage_ws(mw_dycore *h, const StageParams &P0, int in_buf, cuda
 template <int NT>
 static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st, bool last) {
   if constexpr (NT <= 1) { if (tile_variant(NT) == 3) return launch_stage_ws<NT, 3>(h, P, in_buf, st, last); }
+  if constexpr (NT <= 3) { if (tile_variant(NT) == 4) return launch_stage_ws<NT, 4>(h, P, in_buf, st, last); }
   if constexpr (NT <= 3) { if (tile_variant(NT) == 2) return launch_stage_ws<NT, 2>(h, P, in_buf, st, last); }
   if constexpr (NT <= 1) { if (tile_variant(NT) == 1) return launch_stage_v<NT, 1>(h, P, in_buf, st); }
   return launch_stage_v<NT, 0>(h, P, in_buf, st);
@@ -802,17 +809,21 @@ extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields
   }
   const int variant = tile_variant(c.num_tracers);
   const int ncycles = (int) ceil(dt_phys / mw_dycore_compute_time_step(h));                 // DYC:104-108
-  const bool pipelined = rows_per_slab >= 8 && c.nproc_x * c.nproc_y == 1 && !h->comm && c.ny_glob > 1 && variant == 2 &&
+  const bool pipelined = rows_per_slab >= 8 && c.nproc_x * c.nproc_y == 1 && !h->comm && c.ny_glob > 1 && (variant == 2 || variant == 4) &&
                          c.ny / rows_per_slab >= 4;
   if (pipelined) {
     MW_CUDA_OK(cudaDeviceSynchronize());                  // the non-blocking streams do not order against earlier default-stream work
     int rc = 1;
+#define MW_HOST_PIPE(NT)                                                                                          \
+  rc = variant == 4 ? host_step_pipelined<NT, 4>(h, host_fields, dt_phys, rows_per_slab, ncycles)                 \
+                    : host_step_pipelined<NT, 2>(h, host_fields, dt_phys, rows_per_slab, ncycles)
     switch (c.num_tracers) {
-      case 0: rc = host_step_pipelined<0, 2>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
-      case 1: rc = host_step_pipelined<1, 2>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
-      case 2: rc = host_step_pipelined<2, 2>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
-      case 3: rc = host_step_pipelined<3, 2>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
+      case 0: MW_HOST_PIPE(0); break;
+      case 1: MW_HOST_PIPE(1); break;
+      case 2: MW_HOST_PIPE(2); break;
+      case 3: MW_HOST_PIPE(3); break;
     }
+#undef MW_HOST_PIPE
     if (rc != 1) return rc;                               // 1 = grid too small for the chain: unpipelined path below
   }
   for (int f = 0; f < h->N; ++f) MW_CUDA_OK(cudaMemcpyAsync(h->dev_fields[f], host_fields[f], bytes, cudaMemcpyHostToDevice, 0));

@@ -69,14 +69,15 @@ __device__ __forceinline__ double fast_rcp1(double x) {
 struct WenoConsts { double c133, c524, k2, k2e, k3, k4, i12, i24, tenth, e20; };
 __constant__ WenoConsts wc = {13.0 / 3.0, 5.0 / 24.0, 13.0 / 192.0, 7.0 / 160.0, 3129.0 / 2880.0, 87617.0 / 20160.0,
                               1.0 / 12.0, 1.0 / 24.0, 0.1, 1.e-20};
-__device__ __forceinline__ void weno5_edges(double s0, double s1, double s2, double s3, double s4,
-                                            double &v_lo, double &v_hi) {
-  const double d01 = s1 - s0, d12 = s2 - s1, d23 = s3 - s2, d34 = s4 - s3;
-  const double DL = d12 - d01, DC = d23 - d12, DR = d34 - d23;               // second differences
+// The part of the reconstruction after the differences: centre value s2, the two inner first differences, the three
+// second differences and Q = (13/3 * D) * D of each.  weno5_edges (one stencil) and weno5_segment (a run of consecutive
+// cells along a line, which shares the differences between neighbouring stencils) both end here, so they give the same bits.
+__device__ __forceinline__ void weno5_core(double s2, double d12, double d23, double DL, double DC, double DR,
+                                           double QL, double QC, double QR, double &v_lo, double &v_hi) {
   const double b1L = fma(2.0, d12, DL), b1C = d12 + d23, b1R = fma(2.0, d23, -DR);
-  const double tL = fma(b1L, b1L, (wc.c133 * DL) * DL);                      // 4*TV of the three quadratics
-  const double tC = fma(b1C, b1C, (wc.c133 * DC) * DC);
-  const double tR = fma(b1R, b1R, (wc.c133 * DR) * DR);
+  const double tL = fma(b1L, b1L, QL);                                       // 4*TV of the three quadratics
+  const double tC = fma(b1C, b1C, QC);
+  const double tR = fma(b1R, b1R, QR);
   const double T3 = DR - DL, E4 = fma(-2.0, DC, DL + DR);                    // third / fourth difference
   const double b1H = fma(-wc.c524, T3, b1C);
   const double c2 = fma(8.0, DC, -E4);
@@ -104,6 +105,24 @@ __device__ __forceinline__ void weno5_edges(double s0, double s1, double s2, dou
   od = (inv * 0.25) * od;
   v_lo = ev - od;
   v_hi = ev + od;
+}
+__device__ __forceinline__ void weno5_edges(double s0, double s1, double s2, double s3, double s4,
+                                            double &v_lo, double &v_hi) {
+  const double d01 = s1 - s0, d12 = s2 - s1, d23 = s3 - s2, d34 = s4 - s3;
+  const double DL = d12 - d01, DC = d23 - d12, DR = d34 - d23;               // second differences
+  weno5_core(s2, d12, d23, DL, DC, DR, (wc.c133 * DL) * DL, (wc.c133 * DC) * DC, (wc.c133 * DR) * DR, v_lo, v_hi);
+}
+// NJ consecutive cells of a line from their NJ + 4 values: cell c uses s[c .. c+4].  First and second differences and the
+// 13/3 D^2 terms are formed once per value instead of once per stencil (9 fewer fp64 operations per cell).
+template <int NJ>
+__device__ __forceinline__ void weno5_segment(const double (&s)[NJ + 4], double (&lo)[NJ], double (&hi)[NJ]) {
+  double d[NJ + 3], D[NJ + 2], Q[NJ + 2];
+#pragma unroll
+  for (int j = 0; j < NJ + 3; ++j) d[j] = s[j + 1] - s[j];
+#pragma unroll
+  for (int j = 0; j < NJ + 2; ++j) { D[j] = d[j + 1] - d[j]; Q[j] = (wc.c133 * D[j]) * D[j]; }
+#pragma unroll
+  for (int c = 0; c < NJ; ++c) weno5_core(s[c + 2], d[c + 1], d[c + 2], D[c], D[c + 1], D[c + 2], Q[c], Q[c + 1], Q[c + 2], lo[c], hi[c]);
 }
 
 // ----------------------------------------------------------------------------------------------------------

@@ -58,24 +58,35 @@ struct WsCfg {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Blocking wait on an mbarrier phase.  try_wait suspends the thread in hardware until the phase completes or the time hint
+// (ns) expires, so a waiting warp costs a handful of issue slots per hint period instead of polling -- issue slots are what
+// the reconstruction warps are short of.  A lost hand-off must fail loudly, not hang the GPU: trap after 4M wake-ups.
 __device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0;
+  const uint32_t a = smem_u32(bar), hint = 20000u;
   for (int spin = 0; !done; ++spin) {
     asm volatile(
         "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(a), "r"(parity), "r"(hint)
         : "memory");
-    if (spin > (1 << 22)) __trap();                        // a lost hand-off must fail loudly, not hang the GPU
+    if (spin > (1 << 22)) __trap();
   }
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-template <int NT, int TX, int TY>
+// SEG = true: the x / y reconstructions are handed out as line segments instead of single stencils: an x segment is 6
+// consecutive cells of one row (10 values), a y segment 5 consecutive cells of one column (9 values), one segment per lane,
+// fully unrolled with compile-time strides, sharing the differences of neighbouring stencils (weno5_segment).  Against the
+// per-stencil job loop that is 1.7 instead of 5 shared-memory loads and no descriptor decode per reconstruction, and 9 fewer
+// fp64 operations.  Whole warps take "loads" of 32 segments (y: one variable, both halves, 16 columns; x: 32 consecutive
+// (variable, row, third) triples); thread 0 deals the loads to the 12 reconstruction warps so that the four SM
+// sub-partitions (warp w runs on sub-partition w % 4) get equal work.
+template <int NT, int TX, int TY, bool SEG = false>
 __global__ void __launch_bounds__(4 * TX * TY, 1)
 k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
   using C = WsCfg<NT, TX, TY>;
@@ -102,6 +113,37 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
     mbar_init(&empty_bar[0], C::NU); mbar_init(&empty_bar[1], C::NU);
     mbar_fence_init();
     tma_prefetch_desc(&tmap);
+    if constexpr (SEG) {
+      // deal the segment loads: ids [0, N) = y loads (variable id), [N, N + NXL) = x loads; cost in tenths of a reconstruction
+      static_assert(TX == 16 && (TX + 2) % 6 == 0 && (TY + 2) % 5 == 0, "segment lengths assume a 16 x 8 tile");
+      constexpr int NXS = N * TY * ((TX + 2) / 6), NXL = (NXS + 31) / 32, XPV = TY * ((TX + 2) / 6);
+      int *asg = reinterpret_cast<int *>(sm + C::OFF_DESC);        // [12 warps][SEG_ROUNDS + 1]: count, then load ids
+      int smsp[4] = {0, 0, 0, 0}, wl[12], cnt[12];
+      for (int w = 0; w < 12; ++w) { wl[w] = w < 8 ? 30 : 0; cnt[w] = 0; }
+      const int ny_loads = P.sim2d ? 0 : N;
+      bool used[N + NXL];
+      for (int i = 0; i < N + NXL; ++i) used[i] = false;
+      for (int n = 0; n < ny_loads + NXL; ++n) {
+        int best = -1, bc = -1;
+        for (int id = (P.sim2d ? N : 0); id < N + NXL; ++id) {
+          if (used[id]) continue;
+          int c;
+          if (id < N) c = 50 + (id == idT ? 22 : 0);
+          else { const int p0 = (id - N) * 32; c = 60 + ((p0 < (idT + 1) * XPV && p0 + 32 > idT * XPV) ? 26 : 0); }
+          if (c > bc) { bc = c; best = id; }
+        }
+        used[best] = true;
+        int sb = 0;
+        for (int q = 1; q < 4; ++q) if (smsp[q] < smsp[sb]) sb = q;
+        int wb = sb + 8;                                            // prefer the helper warp, then the lighter owner warp
+        if (cnt[wb] >= 1 && wl[sb] <= wl[wb]) wb = sb;
+        if (wl[sb + 4] < wl[wb]) wb = sb + 4;
+        if (wl[sb] < wl[wb]) wb = sb;
+        asg[wb * 8 + 1 + cnt[wb]] = best;
+        cnt[wb]++; wl[wb] += bc; smsp[sb] += bc;
+      }
+      for (int w = 0; w < 12; ++w) asg[w * 8] = cnt[w];
+    }
   }
   __syncthreads();
 
@@ -124,6 +166,7 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
     }
     // static schedule of my x/y reconstruction jobs: rounds [0, QO) are shared by all R threads, rounds [QO, QH) belong
     // to the helpers.  Jobs are ordered (rho*theta)' first (those also evaluate the edge pressures), then the others.
+    if constexpr (!SEG)
     for (int m = 0; m < C::QH; ++m) {
       int j = -1;
       if (m < C::QO) j = m * NR + tid;
@@ -260,8 +303,90 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
         for (int v = 0; v < NH; ++v) vhi_prev[v] = vhi[v];
         p_hi_prev = p_hi;
       }
+      // ---- x / y reconstructions of level k ----
+      if constexpr (SEG) {
+        const double *Wk = W + (k % NSLOT) * C::SLOTP;
+        const double hytc_k = __ldg(P.hytc + k), ihytc_k = __ldg(P.ihytc + k), pcell_k = __ldg(P.pcell + k);
+        mbar_wait_spin(&tma_bar[k % NSLOT], (uint32_t) ((k / NSLOT) & 1));
+        constexpr int EP = (N * 2 - idT * 2) * PER;         // from a (rho*theta)' edge value to its pressure slot
+        constexpr int XPV = TY * ((TX + 2) / 6), NXS = N * XPV;
+        const int *asg = reinterpret_cast<const int *>(sm + C::OFF_DESC) + (tid >> 5) * 8;
+        const int lane = tid & 31, nload = asg[0];
+#pragma unroll 1
+        for (int r = 0; r < nload; ++r) {
+          const int id = asg[1 + r];
+          // my segment of this load: `cnt` consecutive cells of a line, values src[0 .. cnt+3] at stride st, results to
+          // e[0], e[PER] (+ the pressures for (rho*theta)') at stride est
+          int l, cnt, st, est;
+          const double *src;
+          double *e;
+          bool valid = true;
+          if (id < N) {                                     // y load: variable id, lane = (half, column)
+            const int x = lane % TX, sy = lane / TX;
+            l = id; cnt = 5; st = PX; est = TX;
+            src = Wk + l * PLANE + (5 * sy) * PX + (x + HALO);
+            e = E + (l * 2) * PER + C::XC + (5 * sy) * TX + x;
+          } else {                                          // x load: 32 consecutive (variable, row, third) triples
+            const int p = (id - N) * 32 + lane;
+            valid = p < NXS;
+            const int pc = valid ? p : NXS - 1;
+            l = pc / XPV;
+            const int rem = pc - l * XPV, y = rem / 3, sx = rem - 3 * y;
+            cnt = valid ? 6 : 0; st = 1; est = 1;
+            src = Wk + l * PLANE + (y + HALO) * PX + 6 * sx;
+            e = E + (l * 2) * PER + y * (TX + 2) + 6 * sx;
+          }
+          const bool ist = (l == idT);
+          // Sliding stencil along the line, two cells at a time (two independent reconstructions in flight, like the
+          // per-stencil job loop).  State: the centre value and the two above it, three first differences, three second
+          // differences and their 13/3 D^2 terms; a pair loads two new values and shifts the state by two.
+          double s2 = src[2 * st], s3 = src[3 * st], s4 = src[4 * st];
+          double d12, d23 = s3 - s2, d34 = s4 - s3, DL, DC, DR;
+          {
+            const double sa = src[0], sb = src[st];
+            const double d01 = sb - sa;
+            d12 = s2 - sb;
+            DL = d12 - d01; DC = d23 - d12; DR = d34 - d23;
+          }
+          double QL = (wc.c133 * DL) * DL, QC = (wc.c133 * DC) * DC, QR = (wc.c133 * DR) * DR;
+          const double *nxt = src + 5 * st;
+          int c = 0;
+#pragma unroll 1
+          for (; c + 1 < cnt; c += 2) {
+            const double sn0 = nxt[0], sn1 = nxt[st];       // sn1 is beyond the segment in its last pair: loaded, never used
+            nxt += 2 * st;
+            const double dn0 = sn0 - s4, dn1 = sn1 - sn0;
+            const double Dn0 = dn0 - d34, Dn1 = dn1 - dn0;
+            const double Qn0 = (wc.c133 * Dn0) * Dn0, Qn1 = (wc.c133 * Dn1) * Dn1;
+            double loA, hiA, loB, hiB;
+            weno5_core(s2, d12, d23, DL, DC, DR, QL, QC, QR, loA, hiA);
+            weno5_core(s3, d23, d34, DC, DR, Dn0, QC, QR, Qn0, loB, hiB);
+            e[0] = loA; e[PER] = hiA; e[est] = loB; e[PER + est] = hiB;
+            if (ist) {
+              e[EP] = eos_pressure(loA, hytc_k, ihytc_k, pcell_k, P);
+              e[EP + PER] = eos_pressure(hiA, hytc_k, ihytc_k, pcell_k, P);
+              e[EP + est] = eos_pressure(loB, hytc_k, ihytc_k, pcell_k, P);
+              e[EP + PER + est] = eos_pressure(hiB, hytc_k, ihytc_k, pcell_k, P);
+            }
+            e += 2 * est;
+            s2 = s4; s3 = sn0; s4 = sn1;
+            d12 = d34; d23 = dn0; d34 = dn1;
+            DL = DR; DC = Dn0; DR = Dn1;
+            QL = QR; QC = Qn0; QR = Qn1;
+          }
+          if (c < cnt) {                                    // odd cell at the end of a y segment
+            double loA, hiA;
+            weno5_core(s2, d12, d23, DL, DC, DR, QL, QC, QR, loA, hiA);
+            e[0] = loA; e[PER] = hiA;
+            if (ist) {
+              e[EP] = eos_pressure(loA, hytc_k, ihytc_k, pcell_k, P);
+              e[EP + PER] = eos_pressure(hiA, hytc_k, ihytc_k, pcell_k, P);
+            }
+          }
+        }
+      } else {
       // ---- x / y reconstruction jobs of level k from my schedule: pairs (two interleaved for ILP), then an odd one ----
-      {
+
         const double *Wk = W + (k % NSLOT) * C::SLOTP;
         const double hytc_k = __ldg(P.hytc + k), ihytc_k = __ldg(P.ihytc + k), pcell_k = __ldg(P.pcell + k);
         mbar_wait_spin(&tma_bar[k % NSLOT], (uint32_t) ((k / NSLOT) & 1));
