@@ -399,7 +399,7 @@ def main():
                         "api": "mw_dycore_time_step_host (pinned host buffers)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "k_stage_ws", "kernel_ms": k_ms, "peak_source": peak_src,
+                             "traffic": traffic, "kernel": "k_stage_ws<1,16,8,SEG>", "kernel_ms": k_ms, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                              "note": "the fused stage kernel is FP64-pipe-bound, not HBM-bound (DESIGN.md section 4): "
                                      "the binding roofline is reported under fp64_pipe",

@@ -84,13 +84,16 @@ template <int NT, int VAR> struct Tile {
 };
 // Variant 2: warp-specialised kernel (stage_ws.cuh), 16 x 8 tile, reconstruction and update warps run concurrently.
 static int tile_variant(int nt) {
-  static int v = -1;
-  if (v < 0) {
+  static int v = -2;
+  if (v == -2) {
     const char *e = getenv("MW_TILE_VARIANT");
-    v = e ? atoi(e) : 2;                               // default: the warp-specialised kernel
+    v = e ? atoi(e) : -1;                              // -1 = default choice per tracer count (below)
     const char *t = getenv("MW_NO_TMA");
     if (t && atoi(t) != 0) v = 0;                           // the plain-load path exists in the phase kernel only
   }
+  // default: the warp-specialised kernel; with <= 1 tracer its segment form (x/y reconstructions as sliding line segments)
+  // is 1.8 % faster, with 3 tracers 1 % slower (profiles/r01n_stage_seg_variant_ncu_summary.txt)
+  if (v == -1) return nt <= 1 ? 4 : (nt <= 3 ? 2 : 0);
   if (v == 4) return nt <= 3 ? 4 : 0;                    // ws kernel with segment reconstructions
   if (v == 3) return nt <= 1 ? 3 : (nt <= 3 ? 2 : 0);    // uniform-jobs kernel (stage_uj.cuh) where it fits in smem
   if (v == 2) return nt <= 3 ? 2 : 0;

@@ -338,29 +338,19 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
           }
           const bool ist = (l == idT);
           // Sliding stencil along the line, two cells at a time (two independent reconstructions in flight, like the
-          // per-stencil job loop).  State: the centre value and the two above it, three first differences, three second
-          // differences and their 13/3 D^2 terms; a pair loads two new values and shifts the state by two.
-          double s2 = src[2 * st], s3 = src[3 * st], s4 = src[4 * st];
-          double d12, d23 = s3 - s2, d34 = s4 - s3, DL, DC, DR;
-          {
-            const double sa = src[0], sb = src[st];
-            const double d01 = sb - sa;
-            d12 = s2 - sb;
-            DL = d12 - d01; DC = d23 - d12; DR = d34 - d23;
-          }
-          double QL = (wc.c133 * DL) * DL, QC = (wc.c133 * DC) * DC, QR = (wc.c133 * DR) * DR;
+          // per-stencil job loop): the state is the five values of the current stencil; a pair loads two new values and
+          // shifts by two.  (Carrying the differences too saves 9 fp64 operations per cell but costs 12 register moves
+          // per cell for the shift, which is a net loss; unrolling the shift away makes the loop outgrow the I-cache.)
+          double s0 = src[0], s1 = src[st], s2 = src[2 * st], s3 = src[3 * st], s4 = src[4 * st];
           const double *nxt = src + 5 * st;
           int c = 0;
 #pragma unroll 1
           for (; c + 1 < cnt; c += 2) {
-            const double sn0 = nxt[0], sn1 = nxt[st];       // sn1 is beyond the segment in its last pair: loaded, never used
+            const double s5 = nxt[0], s6 = nxt[st];         // s6 is beyond the segment in its last pair: loaded, never used
             nxt += 2 * st;
-            const double dn0 = sn0 - s4, dn1 = sn1 - sn0;
-            const double Dn0 = dn0 - d34, Dn1 = dn1 - dn0;
-            const double Qn0 = (wc.c133 * Dn0) * Dn0, Qn1 = (wc.c133 * Dn1) * Dn1;
             double loA, hiA, loB, hiB;
-            weno5_core(s2, d12, d23, DL, DC, DR, QL, QC, QR, loA, hiA);
-            weno5_core(s3, d23, d34, DC, DR, Dn0, QC, QR, Qn0, loB, hiB);
+            weno5_edges(s0, s1, s2, s3, s4, loA, hiA);
+            weno5_edges(s1, s2, s3, s4, s5, loB, hiB);
             e[0] = loA; e[PER] = hiA; e[est] = loB; e[PER + est] = hiB;
             if (ist) {
               e[EP] = eos_pressure(loA, hytc_k, ihytc_k, pcell_k, P);
@@ -369,14 +359,11 @@ k_stage_ws(const __grid_constant__ CUtensorMap tmap, const StageParams P) {
               e[EP + PER + est] = eos_pressure(hiB, hytc_k, ihytc_k, pcell_k, P);
             }
             e += 2 * est;
-            s2 = s4; s3 = sn0; s4 = sn1;
-            d12 = d34; d23 = dn0; d34 = dn1;
-            DL = DR; DC = Dn0; DR = Dn1;
-            QL = QR; QC = Qn0; QR = Qn1;
+            s0 = s2; s1 = s3; s2 = s4; s3 = s5; s4 = s6;
           }
           if (c < cnt) {                                    // odd cell at the end of a y segment
             double loA, hiA;
-            weno5_core(s2, d12, d23, DL, DC, DR, QL, QC, QR, loA, hiA);
+            weno5_edges(s0, s1, s2, s3, s4, loA, hiA);
             e[0] = loA; e[PER] = hiA;
             if (ist) {
               e[EP] = eos_pressure(loA, hytc_k, ihytc_k, pcell_k, P);
