@@ -1,0 +1,107 @@
+"""Size-independent properties at BASELINE.json's full sizes (the oracle cannot run these in seconds): config 2
+(512 x 512 x 128, dry dycore + vapour) and the per-GPU block of config 3's weak form (1024 x 1024 x 128, Kessler tracers).
+  * a horizontally uniform state stays horizontally uniform, bit for bit (every tile, ring and periodic image agrees)
+  * periodic translation commutes with the step, bit for bit (no dependence on where a cell sits in its tile / slab)
+  * domain mass and vapour mass are conserved to round-off (periodic x/y, wall z)
+  * the slab-pipelined host-buffer step equals the device-resident step, bit for bit
+  * the full physics step keeps every field finite and every tracer non-negative"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ZLEN = 20000.0
+
+
+def setup(nx, ny, nz, T, perturb=True):
+    import torch
+    import miniweatherml_b200 as mw
+    cfg = mw.make_config(nx, ny, nz, nx * 1000.0, ny * 1000.0, ZLEN, T)
+    dy = mw.Dycore(cfg)
+    fields = [torch.empty((nz, ny, nx), device="cuda", dtype=torch.float64) for _ in range(5 + T)]
+    dy.init_supercell(fields)
+    if perturb:
+        mw.perturb_temperature(fields[4], 0, 0, 1000.0, 1000.0, ZLEN / nz, nx * 1000.0, ny * 1000.0)
+    return mw, torch, dy, fields
+
+
+def masses(torch, fields, T):
+    tot = fields[0].sum(dtype=torch.float64)
+    for t in range(T):
+        tot = tot + fields[5 + t].sum(dtype=torch.float64)
+    return tot.item(), fields[5].sum(dtype=torch.float64).item()
+
+
+def test_config2_uniform_state_stays_uniform():
+    mw, torch, dy, f = setup(512, 512, 128, 1, perturb=False)
+    dt = dy.compute_time_step()
+    for _ in range(2):
+        dy.time_step(f, dt)
+    torch.cuda.synchronize()
+    for l, a in enumerate(f):
+        assert bool(torch.isfinite(a).all())
+        assert bool((a == a[:, :1, :1]).all()), "field %d is no longer horizontally uniform" % l
+    assert f[3].abs().max().item() < 1e-2                       # the discrete hydrostatic column is nearly at rest (w ~ 4e-5 m/s)
+    dy.close()
+
+
+def test_config2_translation_mass_and_host_pipeline():
+    mw, torch, dy, f = setup(512, 512, 128, 1)
+    dt = dy.compute_time_step()
+    f0 = [a.clone() for a in f]
+    m0 = masses(torch, f, 1)
+    for _ in range(2):
+        dy.time_step(f, dt)
+    torch.cuda.synchronize()
+    m1 = masses(torch, f, 1)
+    assert abs(m1[0] - m0[0]) <= 1e-13 * abs(m0[0]) and abs(m1[1] - m0[1]) <= 1e-13 * abs(m0[1]), (m0, m1)
+    assert f[3].abs().max().item() > 1e-3                       # the thermal is rising: the run is not trivial
+    # translation by an odd number of cells in x and y (not a multiple of the 16 x 8 tile or the 32-row slab)
+    sx, sy = 37, 101
+    g = [torch.roll(a, shifts=(sy, sx), dims=(1, 2)).contiguous() for a in f0]
+    for _ in range(2):
+        dy.time_step(g, dt)
+    torch.cuda.synchronize()
+    for l in range(6):
+        assert torch.equal(g[l], torch.roll(f[l], shifts=(sy, sx), dims=(1, 2))), "field %d: translation does not commute" % l
+    del g
+    # the host-buffer (slab-pipelined) step from the same initial state
+    host = [a.cpu().pin_memory() for a in f0]
+    hnp = [h.numpy() for h in host]
+    l0 = dy.launch_count()
+    for _ in range(2):
+        dy.time_step_host(hnp, dt)
+    assert dy.launch_count() - l0 > 2 * 3 * 8                   # the pipeline ran (many slab launches per operation)
+    for l in range(6):
+        assert torch.equal(host[l], f[l].cpu()), "field %d: host-buffer step differs" % l
+    dy.close()
+
+
+def test_config3_block_full_physics_step():
+    nx = ny = 1024
+    nz = 128
+    mw, torch, dy, f = setup(nx, ny, nz, 3)
+    f[6].zero_(); f[7].zero_()
+    # seed cloud and rain in a slab so that Kessler's branches and the tracer FCT are active
+    f[6][10:30, 200:600, 300:700] = 1.0e-3
+    f[7][0:25, 250:550, 350:650] = 5.0e-4                      # rain down to the lowest level: precl > 0 there
+    precl = torch.zeros((ny, nx), device="cuda", dtype=torch.float64)
+    dt = dy.compute_time_step()
+    dz = ZLEN / nz
+    f5 = [f[0], f[1], f[2], f[4], f[5]]
+    column = mw.column_average(f5)
+    m0 = masses(torch, f, 3)
+    dy.time_step(f, dt)
+    torch.cuda.synchronize()
+    m1 = masses(torch, f, 3)
+    assert abs(m1[0] - m0[0]) <= 1e-13 * abs(m0[0]), (m0, m1)     # the dycore alone conserves total mass
+    rs = mw.kessler_step(f[4], f[0], f[5], f[6], f[7], precl, dz, dt, want_rainsplit=True)
+    mw.sponge_layer(f, dz, ZLEN, dt)
+    mw.nudge_to_column(f5, column, dt)
+    torch.cuda.synchronize()
+    assert rs >= 1
+    for l, a in enumerate(f):
+        assert bool(torch.isfinite(a).all()), l
+    for t in range(3):
+        assert f[5 + t].min().item() >= 0.0
+    assert precl.min().item() >= 0.0 and precl.max().item() > 0.0  # rain reached the ground somewhere
+    dy.close()
