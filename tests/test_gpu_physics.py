@@ -242,3 +242,34 @@ def test_shipped_surrogate_weights_kat(golden, tc):
     for f in range(4):
         assert np.abs(out[f].cpu().numpy() - ref[f]).max() / rngs[f] <= (1e-6 if tc else 1e-12)
     assert np.abs(out[0].cpu().numpy() - fl[0]).max() < 5.0            # temperature after "microphysics" within 5 K of before
+
+
+def test_surrogate_normalisation_matches_fp64_division_at_float_midpoints(golden):
+    """PON:182-186 normalises with an fp64 division and casts to float.  Inputs placed within a few fp64 ulps of float
+    rounding midpoints are where any shortcut (a multiply by 1/(hi-lo), r01t: no faster, not kept) would flip an fp32 input
+    by one ulp -- a 1e-7 error in normalised units; the bound is 1e-12.  Guards the exact-division path."""
+    import miniweatherml_b200 as mw
+    k = golden("ponni_shipped_weights_kat.npz")
+    scl_in, scl_out = k["scl_in"], k["scl_out"]
+    rng = np.random.default_rng(99)
+    n = 40000
+    cols = []
+    for f in range(5):
+        lo, hi = scl_in[f]
+        xf = rng.uniform(0.05, 0.95, n).astype(np.float32)
+        mid = (xf.astype(np.float64) + np.nextafter(xf, np.float32(2)).astype(np.float64)) / 2      # float rounding midpoints
+        q = mid
+        for _ in range(int(1)):
+            steps = rng.integers(-6, 7, n)
+            q = mid + steps * np.spacing(mid)                     # a few fp64 ulps either side
+        v = lo + q * (hi - lo)
+        v[::7] = lo                                               # exact zeros and the interval ends too
+        v[3::11] = hi
+        cols.append(np.ascontiguousarray(v))
+    ref = O.surrogate(k["w"], scl_in, scl_out, *cols)
+    for tc in (False, True):
+        out = mw.surrogate_forward(k["w"], scl_in, scl_out, *[dev(x) for x in cols], use_tensor_cores=tc)
+        rngs = scl_out[:, 1] - scl_out[:, 0]
+        for f in range(4):
+            err = np.abs(out[f].cpu().numpy() - ref[f]).max() / rngs[f]
+            assert err <= (1e-6 if tc else 1e-12), (tc, f, err)
