@@ -571,7 +571,8 @@ static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaSt
   if (h->timing) { ensure_events(2); cudaEventRecord(h->ev[0], st); }
 
   Q.S.qout = h->q[0];
-  k_coupler_to_dyn<NT><<<cgrid, 256, 0, st>>>(Q);
+  const unsigned cvgrid = (unsigned) ((ncell + 256 * CONV_CPT - 1) / (256 * CONV_CPT));      // CONV_CPT cells per thread
+  k_coupler_to_dyn<NT><<<cvgrid, 256, 0, st>>>(Q);
   MW_CUDA_OK(cudaGetLastError());
   h->launches++;
   {
@@ -596,7 +597,7 @@ static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaSt
     }
   }
   Q.S.qin = h->q[0];
-  k_dyn_to_coupler<NT><<<cgrid, 256, 0, st>>>(Q);
+  k_dyn_to_coupler<NT><<<cvgrid, 256, 0, st>>>(Q);
   MW_CUDA_OK(cudaGetLastError());
   h->launches++;
   if (h->timing) cudaEventRecord(h->ev[1], st);
@@ -714,15 +715,16 @@ static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double 
     const int j0 = r0, j1 = std::min(r1, c.ny), nj = j1 - j0;
     const int ta = r0 / 8, tb = r1 > c.ny ? nby + (r1 - c.ny) / 8 : (r1 + 7) / 8;           // stage kernels: whole tile rows
     const unsigned cgrid = (unsigned) (((long long) c.nz * nj * c.nx + 255) / 256);
+    const unsigned cvgrid = (unsigned) (((long long) c.nz * nj * c.nx + 256 * CONV_CPT - 1) / (256 * CONV_CPT));
     const Link &lk = chain[l];
     if (lk.kind == 0) {
       ConvertParams q = Q;
       q.S.qout = h->q[0]; q.S.jr_lo = j0; q.S.jr_n = nj;
-      k_coupler_to_dyn<NT><<<cgrid, 256, 0, cs>>>(q);
+      k_coupler_to_dyn<NT><<<cvgrid, 256, 0, cs>>>(q);
     } else if (lk.kind == 3) {
       ConvertParams q = Q;
       q.S.qin = h->q[0]; q.S.jr_lo = j0; q.S.jr_n = nj;
-      k_dyn_to_coupler<NT><<<cgrid, 256, 0, cs>>>(q);
+      k_dyn_to_coupler<NT><<<cvgrid, 256, 0, cs>>>(q);
       if (n_done_ev >= (int) h->ev_done.size()) {
         cudaEvent_t e;
         MW_CUDA_OK(cudaEventCreateWithFlags(&e, prof ? cudaEventDefault : cudaEventDisableTiming));

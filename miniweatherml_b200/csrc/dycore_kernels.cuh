@@ -76,9 +76,8 @@ __device__ __forceinline__ void tile_coords(const StageParams &P, int &bx, int &
 // small helpers
 // --------------------------------------------------------------------------------------------------------
 // thread -> cell of the launch's row range; false when out of range.  c = flat index in the full [nz][ny][nx] array
-__device__ __forceinline__ bool range_cell(const StageParams &P, int &k, int &j, int &i, long long &c) {
+__device__ __forceinline__ bool range_cell_at(const StageParams &P, long long t, int &k, int &j, int &i, long long &c) {
   const int nyr = P.jr_n > 0 ? P.jr_n : P.ny;
-  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long) P.nz * nyr * P.nx) return false;
   i = (int) (t % P.nx);
   j = P.jr_lo + (int) ((t / P.nx) % nyr);
@@ -86,6 +85,12 @@ __device__ __forceinline__ bool range_cell(const StageParams &P, int &k, int &j,
   c = ((long long) k * P.ny + j) * P.nx + i;
   return true;
 }
+__device__ __forceinline__ bool range_cell(const StageParams &P, int &k, int &j, int &i, long long &c) {
+  return range_cell_at(P, (long long) blockIdx.x * blockDim.x + threadIdx.x, k, j, i, c);
+}
+// the conversion kernels handle CELLS_PER_THREAD cells a thread, a grid's worth of threads apart (coalescing unchanged),
+// with all loads issued first: twice the bytes in flight per thread for kernels that otherwise wait on memory
+constexpr int CONV_CPT = 2;
 __device__ __forceinline__ void store_with_images(double *var_base, const StageParams &P, int k, int j, int i,
                                                   double v) {
   double *row = var_base + (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + HALO;
@@ -715,57 +720,85 @@ struct ConvertParams {
 template <int NT>
 __global__ void __launch_bounds__(256) k_coupler_to_dyn(const ConvertParams Q) {
   const StageParams &P = Q.S;
-  int i, j, k;
-  long long c;
-  if (!range_cell(P, k, j, i, c)) return;
-  const double rho_d = Q.fields[0][c], u = Q.fields[1][c], v = Q.fields[2][c], w = Q.fields[3][c], temp = Q.fields[4][c];
-  double trv[NT > 0 ? NT : 1];
-  double rho = rho_d;
+  const long long t0 = (long long) blockIdx.x * blockDim.x + threadIdx.x, tstride = (long long) gridDim.x * blockDim.x;
+  int i[CONV_CPT], j[CONV_CPT], k[CONV_CPT];
+  long long c[CONV_CPT];
+  bool ok[CONV_CPT];
+  double f5[CONV_CPT][NUM_STATE], trv[CONV_CPT][NT > 0 ? NT : 1];
 #pragma unroll
-  for (int tr = 0; tr < NT; ++tr) {
-    trv[tr] = Q.fields[NUM_STATE + tr][c];
-    if ((Q.adds_mass_mask >> tr) & 1u) rho += trv[tr];
+  for (int u = 0; u < CONV_CPT; ++u) {
+    ok[u] = range_cell_at(P, t0 + u * tstride, k[u], j[u], i[u], c[u]);
+    if (ok[u]) {
+#pragma unroll
+      for (int l = 0; l < NUM_STATE; ++l) f5[u][l] = __ldg(Q.fields[l] + c[u]);
+#pragma unroll
+      for (int tr = 0; tr < NT; ++tr) trv[u][tr] = __ldg(Q.fields[NUM_STATE + tr] + c[u]);
+    }
   }
-  double rho_v = 0.0;
 #pragma unroll
-  for (int tr = 0; tr < NT; ++tr) if (tr == Q.idWV) rho_v = trv[tr];
-  const double press = rho_d * Q.R_d * temp + rho_v * Q.R_v * temp;
-  const double rt = pow(press / P.C0, 1.0 / P.gamma);          // rho*theta
-  store_with_images(P.qout + (long long) idR * P.vstride, P, k, j, i, rho - __ldg(P.hyc + k));
-  store_with_images(P.qout + (long long) idU * P.vstride, P, k, j, i, u);
-  store_with_images(P.qout + (long long) idV * P.vstride, P, k, j, i, v);
-  store_with_images(P.qout + (long long) idW * P.vstride, P, k, j, i, w);
-  store_with_images(P.qout + (long long) idT * P.vstride, P, k, j, i, rt - __ldg(P.hytc + k));
-  const double r = 1.0 / rho;
+  for (int u = 0; u < CONV_CPT; ++u) {
+    if (!ok[u]) continue;
+    const double rho_d = f5[u][0], temp = f5[u][4];
+    double rho = rho_d;
 #pragma unroll
-  for (int tr = 0; tr < NT; ++tr)
-    store_with_images(P.qout + (long long) (NUM_STATE + tr) * P.vstride, P, k, j, i, trv[tr] * r);
+    for (int tr = 0; tr < NT; ++tr)
+      if ((Q.adds_mass_mask >> tr) & 1u) rho += trv[u][tr];
+    double rho_v = 0.0;
+#pragma unroll
+    for (int tr = 0; tr < NT; ++tr) if (tr == Q.idWV) rho_v = trv[u][tr];
+    const double press = rho_d * Q.R_d * temp + rho_v * Q.R_v * temp;
+    const double rt = pow(press / P.C0, 1.0 / P.gamma);          // rho*theta
+    store_with_images(P.qout + (long long) idR * P.vstride, P, k[u], j[u], i[u], rho - __ldg(P.hyc + k[u]));
+    store_with_images(P.qout + (long long) idU * P.vstride, P, k[u], j[u], i[u], f5[u][1]);
+    store_with_images(P.qout + (long long) idV * P.vstride, P, k[u], j[u], i[u], f5[u][2]);
+    store_with_images(P.qout + (long long) idW * P.vstride, P, k[u], j[u], i[u], f5[u][3]);
+    store_with_images(P.qout + (long long) idT * P.vstride, P, k[u], j[u], i[u], rt - __ldg(P.hytc + k[u]));
+    const double r = 1.0 / rho;
+#pragma unroll
+    for (int tr = 0; tr < NT; ++tr)
+      store_with_images(P.qout + (long long) (NUM_STATE + tr) * P.vstride, P, k[u], j[u], i[u], trv[u][tr] * r);
+  }
 }
 
 template <int NT>
 __global__ void __launch_bounds__(256) k_dyn_to_coupler(const ConvertParams Q) {
   const StageParams &P = Q.S;
-  int i, j, k;
-  long long c;
-  if (!range_cell(P, k, j, i, c)) return;
-  const long long h = (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + i + HALO;
+  const long long t0 = (long long) blockIdx.x * blockDim.x + threadIdx.x, tstride = (long long) gridDim.x * blockDim.x;
   const double *q = P.qin;
-  const double rho = q[h] + __ldg(P.hyc + k);
-  const double rt = q[(long long) idT * P.vstride + h] + __ldg(P.hytc + k);
-  const double press = P.C0 * pow(rt, P.gamma);
-  double rho_d = rho, rho_v = 0.0;
+  int k[CONV_CPT];
+  long long c[CONV_CPT];
+  bool ok[CONV_CPT];
+  double qv[CONV_CPT][NUM_STATE + NT];
 #pragma unroll
-  for (int tr = 0; tr < NT; ++tr) {
-    const double m = q[(long long) (NUM_STATE + tr) * P.vstride + h] * rho;
-    Q.fields[NUM_STATE + tr][c] = m;
-    if ((Q.adds_mass_mask >> tr) & 1u) rho_d -= m;
-    if (tr == Q.idWV) rho_v = m;
+  for (int u = 0; u < CONV_CPT; ++u) {
+    int i, j;
+    ok[u] = range_cell_at(P, t0 + u * tstride, k[u], j, i, c[u]);
+    if (ok[u]) {
+      const long long h = (long long) k[u] * P.zstride + (long long) (j + HALO) * P.pitch + i + HALO;
+#pragma unroll
+      for (int l = 0; l < NUM_STATE + NT; ++l) qv[u][l] = __ldg(q + (long long) l * P.vstride + h);
+    }
   }
-  Q.fields[0][c] = rho_d;
-  Q.fields[1][c] = q[(long long) idU * P.vstride + h];
-  Q.fields[2][c] = q[(long long) idV * P.vstride + h];
-  Q.fields[3][c] = q[(long long) idW * P.vstride + h];
-  Q.fields[4][c] = press / (rho_d * Q.R_d + rho_v * Q.R_v);
+#pragma unroll
+  for (int u = 0; u < CONV_CPT; ++u) {
+    if (!ok[u]) continue;
+    const double rho = qv[u][idR] + __ldg(P.hyc + k[u]);
+    const double rt = qv[u][idT] + __ldg(P.hytc + k[u]);
+    const double press = P.C0 * pow(rt, P.gamma);
+    double rho_d = rho, rho_v = 0.0;
+#pragma unroll
+    for (int tr = 0; tr < NT; ++tr) {
+      const double m = qv[u][NUM_STATE + tr] * rho;
+      Q.fields[NUM_STATE + tr][c[u]] = m;
+      if ((Q.adds_mass_mask >> tr) & 1u) rho_d -= m;
+      if (tr == Q.idWV) rho_v = m;
+    }
+    Q.fields[0][c[u]] = rho_d;
+    Q.fields[1][c[u]] = qv[u][idU];
+    Q.fields[2][c[u]] = qv[u][idV];
+    Q.fields[3][c[u]] = qv[u][idW];
+    Q.fields[4][c[u]] = press / (rho_d * Q.R_d + rho_v * Q.R_v);
+  }
 }
 
 // --------------------------------------------------------------------------------------------------------
