@@ -709,6 +709,8 @@ static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double 
 
   cudaStream_t cs = h->s_cmp;
   int n_done_ev = 0;
+  const bool multi = h->comm && (h->dir_active[0] || h->dir_active[2]);
+  bool seam = false;                                                       // set for the operations of the seam phase
   // operation `l` of the chain on rows [r0, r1); r1 > ny means the two sides of the seam, rows [r0, ny) and [0, r1 - ny)
   auto run = [&](int l, int r0, int r1) -> int {
     if (r1 <= r0) return MW_OK;
@@ -756,6 +758,19 @@ static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double 
       }
     }
     h->launches++;
+    // Decomposed directions: what the NEXT operation reads across a rank boundary goes to the neighbours right after this
+    // one -- the width-3 halos of the operation's output (after c2d, after the tracer finish, after a stage without
+    // tracers) and the boundary cells' FCT factors (after a stage with tracers).  The existing whole-strip exchanges are
+    // reused: rows this level has not reached yet travel too and are simply exchanged again when they are final.  Every
+    // rank issues the same sequence (equal local sizes are required), so the NCCL calls pair up.
+    if (multi && (seam || h->dir_active[0])) {
+      int rc = MW_OK;
+      if (lk.kind == 0) rc = exchange_halos(h, h->q[0], cs);
+      else if (lk.kind == 1 && NT > 0) rc = exchange_mult(h, cs);
+      else if (chain[l + 1].kind != 3)                        // the last output before d2c is read by nobody else
+        rc = exchange_halos(h, lk.stage == 0 ? h->q[1] : (lk.stage == 1 ? h->q[2] : h->q[0]), cs);
+      if (rc != MW_OK) return rc;
+    }
     return MW_OK;
   };
 
@@ -769,6 +784,10 @@ static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double 
       if (nh > hi[l]) { int rc = run(l, hi[l], nh); if (rc != MW_OK) return rc; hi[l] = nh; }
     }
   }
+  seam = true;
+  // the rows next to a y rank boundary read the neighbour's rows instead of the periodic images: halos of the converted
+  // state first (the main phase only exchanged them when x is decomposed), then level by level inside run()
+  if (multi && !h->dir_active[0]) { int rc = exchange_halos(h, h->q[0], cs); if (rc != MW_OK) return rc; }
   for (int l = 1; l < L; ++l) {                                            // the seam region, level by level
     int rc = MW_OK;
     if (chain[l].kind == 1) rc = run(l, cap[l], c.ny + off[l]);            // stage kernel: both sides in one launch
@@ -814,7 +833,10 @@ extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields
   }
   const int variant = tile_variant(c.num_tracers);
   const int ncycles = (int) ceil(dt_phys / mw_dycore_compute_time_step(h));                 // DYC:104-108
-  const bool pipelined = rows_per_slab >= 8 && c.nproc_x * c.nproc_y == 1 && !h->comm && c.ny_glob > 1 && (variant == 2 || variant == 4) &&
+  // decomposed runs: every rank must walk the same schedule, so the blocks must be equal
+  const bool equal_blocks = c.nproc_x * c.nproc_y == 1 ||
+                            (h->comm && c.nx_glob % c.nproc_x == 0 && c.ny_glob % c.nproc_y == 0 && c.nx == c.nx_glob / c.nproc_x && c.ny == c.ny_glob / c.nproc_y);
+  const bool pipelined = rows_per_slab >= 8 && equal_blocks && c.ny_glob > 1 && (variant == 2 || variant == 4) &&
                          c.ny / rows_per_slab >= 4;
   if (pipelined) {
     MW_CUDA_OK(cudaDeviceSynchronize());                  // the non-blocking streams do not order against earlier default-stream work

@@ -22,6 +22,7 @@ def main():
     rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     nxg, nyg, T, steps = [int(a) for a in sys.argv[1:5]]
     physics = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    host = int(sys.argv[6]) if len(sys.argv) > 6 else 0          # also run the slab-pipelined host-buffer step on every rank
     torch.cuda.set_device(lrank)
     dev = torch.device("cuda", lrank)
     dist.init_process_group("nccl", device_id=dev)
@@ -57,6 +58,20 @@ def main():
             mw.sponge_layer(f, dz, zlen, dt, nxy_glob=nglob, comm=comm)
             mw.nudge_to_column([f[i] for i in idx], column, dt, nxy_glob=nglob, comm=comm)
     torch.cuda.synchronize()
+    host_equal = None
+    if host:
+        # mw_dycore_time_step_host on the decomposed grid: uploads, kernels, halo / FCT-factor exchanges and downloads
+        # pipelined slab by slab; must reproduce the device-resident step bit for bit on every rank
+        os.environ["MW_HOST_SLAB_ROWS"] = "8"
+        hf = [np.ascontiguousarray(loc[l]).copy() for l in range(5 + T)]
+        l0 = dy.launch_count()
+        for _ in range(steps):
+            dy.time_step_host(hf, dt)
+        pipelined = dy.launch_count() - l0 > 3 * steps * (2 + 3 * (2 if T else 1))
+        eq = all(np.array_equal(hf[l], f[l].cpu().numpy()) for l in range(5 + T))
+        flags = torch.tensor([int(eq), int(pipelined)], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        host_equal = [bool(flags[0].item()), bool(flags[1].item())]
     # gather blocks on rank 0
     mine = torch.stack(f).contiguous()
     shapes = [None] * world
@@ -85,7 +100,8 @@ def main():
             den = max(np.abs(ref[l]).max(), 1e-300)
             errs.append(float(np.abs(out[l] - ref[l]).max() / den))
         print(json.dumps({"world": world, "grid": [nxg, nyg, nz], "decomp": [npx, npy], "tracers": T, "steps": steps,
-                          "physics": physics, "max_rel_err": errs, "ok": bool(max(errs) <= 1e-9)}), flush=True)
+                          "physics": physics, "max_rel_err": errs, "host_step_equal_and_pipelined": host_equal,
+                          "ok": bool(max(errs) <= 1e-9) and (host_equal is None or all(host_equal))}), flush=True)
     else:
         dist.send(mine, dst=0)
     dist.barrier()

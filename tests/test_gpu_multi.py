@@ -31,3 +31,14 @@ def test_decomposition_independence(nproc, nxg, nyg, T, physics):
         pytest.skip("needs %d GPUs" % nproc)
     r = _run(nproc, [nxg, nyg, T, 3, physics], 29500 + nproc)
     assert r["ok"], r
+
+
+@pytest.mark.parametrize("nproc,nxg,nyg,T", [(2, 48, 160, 1), (2, 48, 160, 2), (4, 64, 160, 3)])
+def test_pipelined_host_step_on_a_decomposed_grid(nproc, nxg, nyg, T):
+    """mw_dycore_time_step_host with rank neighbours (y only at 2 ranks, x and y at 4): slab-pipelined with the halo and
+    FCT-factor exchanges in the schedule, bit-identical to the device-resident step and within 1e-9 of the oracle"""
+    if _ngpu() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    r = _run(nproc, [nxg, nyg, T, 2, 0, 1], 29600 + nproc + T)
+    assert r["host_step_equal_and_pipelined"] == [True, True], r
+    assert r["ok"], r
