@@ -102,6 +102,12 @@ double mw_dycore_compute_time_step(const mw_dycore *h);
 int  mw_dycore_time_step(mw_dycore *h, double *const *fields, double dt_phys, void *stream);
 /* same through HOST buffers: H2D of the 5+T fields, the step, D2H of the results; synchronous */
 int  mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields, double dt_phys);
+/* the schedule mw_dycore_time_step_host walks when it pipelines uploads, kernels and downloads slab by slab (pure host
+ * logic, no device needed): ops6 receives n_ops rows of (level, kind, stage, r0, r1, after_upload) -- kind 0 coupler->dycore,
+ * 1 stage kernel, 2 tracer finish, 3 dycore->coupler; rows [r0, r1), r1 > ny = both sides of the periodic seam; after_upload =
+ * slab upload the operation waits for, -1 = seam phase.  n_ops = 0 when ny is too small for the chain (serial path). */
+int  mw_host_pipeline_plan(int ny, int rows_per_slab, int num_tracers, int ncycles, int *ops6, int max_ops, int *n_ops,
+                           int *n_slabs);
 /* supercell initial condition (hydrostatic GLL-quadrature column + cell averages) straight into coupler fields
  * and into the handle's background profiles */
 int  mw_dycore_init_supercell(mw_dycore *h, double *const *fields, void *stream);

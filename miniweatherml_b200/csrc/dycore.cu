@@ -636,23 +636,23 @@ extern "C" int mw_dycore_time_step(mw_dycore *h, double *const *fields, double d
 // and the periodic images); events tie that stream to the two copy streams.  Results are bit-identical to
 // mw_dycore_time_step on device-resident fields (tests/test_gpu_dycore.py::test_host_step_pipelined_bit_identical).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int NT, int KIND>
-static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double dt_phys, int rows_per_slab, int ncycles) {
-  using K = WsKernel<NT, KIND>;
-  const mw_config &c = h->cfg;
-  static bool attr_set = false;
-  if (!attr_set) { MW_CUDA_OK(K::attr()); attr_set = true; }
-  const int nbx = (c.nx + 15) / 16, nby = (c.ny + 7) / 8;
-  const int S = std::max(1, c.ny / rows_per_slab);         // the last slab takes the remainder
-  // ---- the chain of operations ----
-  double dt_dyn = dt_phys / ncycles;                                       // DYC:104-108
-  struct Link { int kind, stage; };                                        // kind: 0 c2d, 1 stage kernel, 2 tracer finish, 3 d2c
-  std::vector<Link> chain;
+// The schedule of the pipelined host step as plain data (pure host logic, exported as mw_host_pipeline_plan so that the CPU
+// test suite can check coverage and dependency order without a GPU).  kind: 0 coupler->dycore, 1 stage kernel, 2 tracer
+// finish, 3 dycore->coupler.  An operation covers rows [r0, r1); r1 > ny means the two sides of the seam, [r0, ny) and
+// [0, r1 - ny).  `after_upload` = index of the slab upload it has to wait for, -1 for the seam phase (after all uploads).
+namespace {
+struct PlanLink { int kind, stage; };
+struct PlanOp { int level, kind, stage, r0, r1, after_upload; };
+}
+static bool host_pipeline_plan(int ny, int rows_per_slab, int num_tracers, int ncycles, std::vector<PlanLink> &chain,
+                               std::vector<int> &off, std::vector<int> &cap, std::vector<PlanOp> &ops, int &S) {
+  chain.clear(); ops.clear();
+  S = std::max(1, ny / rows_per_slab);                                    // the last slab takes the remainder
   chain.push_back({0, 0});
   for (int ic = 0; ic < ncycles; ++ic)
     for (int st = 0; st < 3; ++st) {
       chain.push_back({1, st});
-      if (NT > 0) chain.push_back({2, st});
+      if (num_tracers > 0) chain.push_back({2, st});
     }
   chain.push_back({3, 0});
   const int L = (int) chain.size();
@@ -660,14 +660,62 @@ static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double 
   // cap[l]: where its sweep ends below the seam.  A stage kernel needs its input 3 rows further (stencil halo) and works
   // on whole tile rows (multiples of 8); the tracer finish needs the stage's FCT factors 1 row further; the conversions
   // are cell-local.  With tracers: off = 0, 8, 9, 16, 17, 24, 25, 25.
-  std::vector<int> off(L), cap(L);
-  off[0] = 0; cap[0] = c.ny;
+  off.assign(L, 0); cap.assign(L, ny);
   for (int l = 1; l < L; ++l) {
     if (chain[l].kind == 1)      { off[l] = ((off[l - 1] + HALO + 7) / 8) * 8; cap[l] = ((cap[l - 1] - HALO) / 8) * 8; }
     else if (chain[l].kind == 2) { off[l] = off[l - 1] + 1;                     cap[l] = cap[l - 1] - 1; }
     else                         { off[l] = off[l - 1];                         cap[l] = cap[l - 1]; }
   }
-  if (cap[L - 1] - off[L - 1] < 8) return 1;                               // too few rows for this chain: caller falls back
+  if (cap[L - 1] - off[L - 1] < 8) return false;                           // too few rows for this chain
+  std::vector<int> hi(off);                                                // level l starts at row off[l]
+  for (int s = 0; s < S; ++s) {
+    const bool last = (s == S - 1);
+    const int u = last ? ny : (s + 1) * rows_per_slab;                     // rows uploaded so far
+    for (int l = 0; l < L; ++l) {
+      const int nh = last ? cap[l] : std::min(u - off[l], cap[l]);
+      if (nh > hi[l]) { ops.push_back({l, chain[l].kind, chain[l].stage, hi[l], nh, s}); hi[l] = nh; }
+    }
+  }
+  for (int l = 1; l < L; ++l) {                                            // the seam region, level by level
+    if (chain[l].kind == 1) ops.push_back({l, 1, chain[l].stage, cap[l], ny + off[l], -1});   // stage kernel: both sides in one launch
+    else {
+      if (ny > cap[l]) ops.push_back({l, chain[l].kind, chain[l].stage, cap[l], ny, -1});
+      if (off[l] > 0) ops.push_back({l, chain[l].kind, chain[l].stage, 0, off[l], -1});
+    }
+  }
+  return true;
+}
+
+extern "C" int mw_host_pipeline_plan(int ny, int rows_per_slab, int num_tracers, int ncycles, int *ops6, int max_ops,
+                                     int *n_ops, int *n_slabs) {
+  MW_REQUIRE(ny > 0 && rows_per_slab >= 8 && rows_per_slab % 8 == 0 && num_tracers >= 0 && ncycles >= 1 && n_ops, "mw_host_pipeline_plan: bad argument");
+  std::vector<PlanLink> chain; std::vector<int> off, cap; std::vector<PlanOp> ops; int S = 0;
+  if (!host_pipeline_plan(ny, rows_per_slab, num_tracers, ncycles, chain, off, cap, ops, S)) { *n_ops = 0; if (n_slabs) *n_slabs = S; return MW_OK; }
+  *n_ops = (int) ops.size();
+  if (n_slabs) *n_slabs = S;
+  for (int i = 0; i < (int) ops.size() && i < max_ops && ops6; ++i) {
+    const PlanOp &o = ops[i];
+    const int v[6] = {o.level, o.kind, o.stage, o.r0, o.r1, o.after_upload};
+    for (int q = 0; q < 6; ++q) ops6[6 * i + q] = v[q];
+  }
+  return MW_OK;
+}
+
+template <int NT, int KIND>
+static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double dt_phys, int rows_per_slab, int ncycles) {
+  using K = WsKernel<NT, KIND>;
+  const mw_config &c = h->cfg;
+  static bool attr_set = false;
+  if (!attr_set) { MW_CUDA_OK(K::attr()); attr_set = true; }
+  const int nbx = (c.nx + 15) / 16, nby = (c.ny + 7) / 8;
+  // ---- the chain of operations and their schedule (host_pipeline_plan above) ----
+  double dt_dyn = dt_phys / ncycles;                                       // DYC:104-108
+  std::vector<PlanLink> chain;
+  std::vector<int> off, cap;
+  std::vector<PlanOp> plan;
+  int S = 0;
+  if (!host_pipeline_plan(c.ny, rows_per_slab, NT, ncycles, chain, off, cap, plan, S)) return 1;   // too few rows: caller falls back
+  const int L = (int) chain.size();
 
   if (!h->s_up) {
     MW_CUDA_OK(cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
@@ -718,7 +766,7 @@ static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double 
     const int ta = r0 / 8, tb = r1 > c.ny ? nby + (r1 - c.ny) / 8 : (r1 + 7) / 8;           // stage kernels: whole tile rows
     const unsigned cgrid = (unsigned) (((long long) c.nz * nj * c.nx + 255) / 256);
     const unsigned cvgrid = (unsigned) (((long long) c.nz * nj * c.nx + 256 * CONV_CPT - 1) / (256 * CONV_CPT));
-    const Link &lk = chain[l];
+    const PlanLink &lk = chain[l];
     if (lk.kind == 0) {
       ConvertParams q = Q;
       q.S.qout = h->q[0]; q.S.jr_lo = j0; q.S.jr_n = nj;
@@ -774,24 +822,18 @@ static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double 
     return MW_OK;
   };
 
-  std::vector<int> hi(off);                                                // level l starts at row off[l]
-  for (int s = 0; s < S; ++s) {
-    MW_CUDA_OK(cudaStreamWaitEvent(cs, h->ev_up[s], 0));
-    const bool last = (s == S - 1);
-    const int u = last ? c.ny : (s + 1) * rows_per_slab;                   // rows uploaded so far
-    for (int l = 0; l < L; ++l) {
-      const int nh = last ? cap[l] : std::min(u - off[l], cap[l]);
-      if (nh > hi[l]) { int rc = run(l, hi[l], nh); if (rc != MW_OK) return rc; hi[l] = nh; }
+  int waited = -1;
+  for (const PlanOp &op : plan) {
+    if (op.after_upload >= 0) {
+      while (waited < op.after_upload) { ++waited; MW_CUDA_OK(cudaStreamWaitEvent(cs, h->ev_up[waited], 0)); }
+    } else if (!seam) {
+      while (waited < S - 1) { ++waited; MW_CUDA_OK(cudaStreamWaitEvent(cs, h->ev_up[waited], 0)); }
+      seam = true;
+      // the rows next to a y rank boundary read the neighbour's rows instead of the periodic images: halos of the converted
+      // state first (the main phase only exchanged them when x is decomposed), then level by level inside run()
+      if (multi && !h->dir_active[0]) { int rc = exchange_halos(h, h->q[0], cs); if (rc != MW_OK) return rc; }
     }
-  }
-  seam = true;
-  // the rows next to a y rank boundary read the neighbour's rows instead of the periodic images: halos of the converted
-  // state first (the main phase only exchanged them when x is decomposed), then level by level inside run()
-  if (multi && !h->dir_active[0]) { int rc = exchange_halos(h, h->q[0], cs); if (rc != MW_OK) return rc; }
-  for (int l = 1; l < L; ++l) {                                            // the seam region, level by level
-    int rc = MW_OK;
-    if (chain[l].kind == 1) rc = run(l, cap[l], c.ny + off[l]);            // stage kernel: both sides in one launch
-    else { rc = run(l, cap[l], c.ny); if (rc == MW_OK) rc = run(l, 0, off[l]); }
+    int rc = run(op.level, op.r0, op.r1);
     if (rc != MW_OK) return rc;
   }
   MW_CUDA_OK(cudaGetLastError());
