@@ -16,6 +16,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 typedef double real;                                   // model/main_header.h:59
@@ -92,6 +93,18 @@ inline void init() { mw::Runtime::get().init(); }
 inline void finalize() { mw::check(mw_fence(), "mw_fence"); }
 inline void fence() { mw::check(mw_fence(), "mw_fence"); }
 inline bool isInitialized() { return mw::Runtime::get().initialised; }
+// the two names the reference's drivers import with using-declarations (driver.cpp:13-14); maxval works on any view that
+// can hand out a host copy (core::View)
+namespace intrinsics {
+template <class T> inline T abs(T v) { return v < 0 ? -v : v; }
+template <class V> inline auto maxval(V const &v) -> typename std::decay<decltype(v.createHostCopy()[0])>::type {
+  auto h = v.createHostCopy();
+  if (h.empty()) endrun("ERROR: maxval of an empty array");
+  auto m = h[0];
+  for (auto const &x : h) if (x > m) m = x;
+  return m;
+}
+}  // namespace intrinsics
 inline void timer_start(char const *label) { mw::Runtime::get().timers[label] = std::chrono::steady_clock::now(); }
 inline void timer_stop(char const *label) {
   auto &r = mw::Runtime::get();
