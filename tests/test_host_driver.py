@@ -73,20 +73,21 @@ REF = os.environ.get("MW_REFERENCE", "/root/reference")
 
 @pytest.mark.needs_reference
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "experiments")), reason="needs /root/reference")
-@pytest.mark.parametrize("exp", ["supercell_example", "simple_city", "community_benchmark"])
+@pytest.mark.parametrize("exp", ["supercell_example/driver.cpp", "simple_city/driver.cpp", "community_benchmark/driver.cpp",
+                                 "supercell_kessler_surrogate/inference_ponni.cpp"])
 def test_reference_drivers_compile_unmodified(tmp_path, exp):
     """The drop-in claim at source level: the reference's OWN driver.cpp, untouched, compiles and links against
     miniweatherml_b200/host/*.h + libmwb200.so -- only the include path differs -- and fails loudly where there is no GPU."""
     build_driver()
-    exe = str(tmp_path / ("ref_" + exp))
+    exe = str(tmp_path / ("ref_" + exp.split("/")[0]))
     cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-I", HOST, "-I", os.path.join(ROOT, "include"),
-           os.path.join(REF, "experiments", exp, "driver.cpp"), "-o", exe, "-L", os.path.join(ROOT, "miniweatherml_b200"), "-lmwb200",
+           os.path.join(REF, "experiments", exp), "-o", exe, "-L", os.path.join(ROOT, "miniweatherml_b200"), "-lmwb200",
            "-Wl,-rpath," + os.path.join(ROOT, "miniweatherml_b200"), "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
     import torch
     if not torch.cuda.is_available():
-        yaml = os.path.join(GOLD, "input_building.yaml" if exp == "simple_city" else "input_config1.yaml")
+        yaml = os.path.join(GOLD, "input_building.yaml" if exp.startswith("simple_city") else "input_config1.yaml")
         r = subprocess.run([exe, yaml], capture_output=True, text=True)
         assert r.returncode != 0 and "no CPU fallback" in r.stderr
 
