@@ -554,7 +554,6 @@ template <int NT>
 static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaStream_t st) {
   const mw_config &c = h->cfg;
   const long long ncell = (long long) c.nz * c.ny * c.nx;
-  const unsigned cgrid = (unsigned) ((ncell + 255) / 256);
   ConvertParams Q;
   memset(&Q, 0, sizeof(Q));
   Q.S = base_params(h);
