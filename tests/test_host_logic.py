@@ -104,3 +104,17 @@ def test_gloo_world_size_2(tmp_path):
            "127.0.0.1", "--master-port", "29611", str(w)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.count("ok") == 2, out.stdout + out.stderr
+
+
+def test_city_layout_matches_the_reference_formula():
+    """mw_city_layout (pure host logic, no device): DYC:1430-1437 for a range of domains, incl. the shipped input_city.yaml"""
+    import ctypes as C
+    import _oracle as O
+    import miniweatherml_b200 as mw
+    L = mw.lib()
+    for xlen, ylen, nx in [(2000., 2000., 400), (1500., 1500., 50), (3000., 2400., 100), (1290., 1470., 43), (5000., 9000., 500)]:
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        assert L.mw_city_layout(xlen, ylen, nx, C.byref(a), C.byref(b), C.byref(c)) == 0
+        assert (a.value, b.value, c.value) == O.city_layout(xlen, ylen, nx)
+    assert O.city_layout(2000., 2000., 400) == (6, 18, 24)       # the shipped case: 6 cells per building, 18 x 24 buildings
+    assert L.mw_city_layout(0., 1., 10, None, None, None) != 0
