@@ -33,7 +33,8 @@ ZLEN = 20000.0
 NUM_TRACERS = 1
 NVAR = 5 + NUM_TRACERS
 BYTES_PER_CELL_UPDATE = 64 * NVAR          # 8 N doubles per cell per SSPRK3 step
-CPU_SAMPLE = dict(nx=128, ny=128, nz=64)   # bounded sample of the same physics for the CPU arm
+CPU_SAMPLE = dict(nx=256, ny=256, nz=128)  # bounded sample of the same workload for the CPU arm: config 2's dz, dt and levels,
+                                           # a quarter of its columns (about 10 s of work for 16 host cores at 6 steps)
 
 
 def measured_peak():
@@ -118,10 +119,10 @@ def cpu_reference_run(steps, warmup, sample=CPU_SAMPLE):
     Returns (cell_updates_per_s, cores, kind, sample_description)."""
     ncores = os.cpu_count() or 1
     nx, ny, nz = sample["nx"], sample["ny"], sample["nz"]
-    desc = "dycore.time_step, supercell %dx%dx%d fp64 (same dx=dy=1000 m, zlen=20 km physics), %d steps" % (nx, ny, nz, steps)
+    desc = "dycore.time_step, supercell %dx%dx%d fp64 (config 2's dx=dy=1000 m, dz, dt and 128 levels; a quarter of its columns), %d steps" % (nx, ny, nz, steps)
     exe = ref_driver(omp=True)
     if exe is not None:
-        env = dict(os.environ, OMP_NUM_THREADS=str(ncores), GATOR_INITIAL_MB="2048")
+        env = dict(os.environ, OMP_NUM_THREADS=str(ncores), GATOR_INITIAL_MB="4096")
 
         def run(nsteps):
             out = subprocess.run([exe, "run", "nx=%d" % nx, "ny=%d" % ny, "nz=%d" % nz, "xlen=%g" % (nx * DX),
@@ -152,16 +153,27 @@ def cpu_reference_run(steps, warmup, sample=CPU_SAMPLE):
     return nx * ny * nz * steps / sec, 1, "port", "oracle/mw_oracle.c dycore step, supercell %dx%dx%d fp64, %d steps, 1 thread" % (nx, ny, nz, steps)
 
 
+def workload_config(world, dt=None):
+    """The `config` object of the benchmark line: the same for both arms (the CPU arm adds the sample it timed)."""
+    npx, npy, _, _ = decomposition(world, 0)
+    nxg, nyg = NX_LOC * npx, NY_LOC * npy
+    if dt is None:
+        dt = 0.6 * min(DX, ZLEN / NZ) / 430.0                      # DYC:70-77
+    return {"workload": "BASELINE configs[1]: dry Euler dycore (WENO5 + SSPRK3, vapour tracer, N=6), synthetic "
+                        "supercell, %dx%dx%d fp64 per GPU" % (NX_LOC, NY_LOC, NZ),
+            "global_grid": [nxg, nyg, NZ], "decomposition": "%dx%d (x,y)" % (npx, npy), "dt": dt,
+            "l2_policy": "state (1.6 GB per GPU) larger than L2, no flush needed"}
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 6))
     v, cores, kind, desc = cpu_reference_run(steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": "cell-updates/s per SSPRK3 step", "value": v, "unit": "cell-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "dry Euler dycore (WENO5+SSPRK3, vapour tracer, N=6), supercell; CPU arm runs a bounded "
-                                   "sample of the same workload", "sample": desc},
+            "config": dict(workload_config(max(args.gpus, 1)), sample=desc),
             "cpu_baseline": {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": v, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -388,11 +400,7 @@ def main():
         line = {"metric": "cell-updates/s per SSPRK3 step", "value": value, "unit": "cell-updates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]: dry Euler dycore (WENO5 + SSPRK3, vapour tracer, N=6), synthetic "
-                                       "supercell, %dx%dx%d fp64 per GPU" % (NX_LOC, NY_LOC, NZ),
-                           "global_grid": [nxg, nyg, NZ], "decomposition": "%dx%d (x,y)" % (npx, npy), "dt": dt,
-                           "l2_policy": "state (1.6 GB per GPU) larger than L2, no flush needed",
-                           "state_finite": finite},
+                "config": dict(workload_config(world, dt), state_finite=finite),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": NVAR * field_bytes,
                         "d2h_bytes_per_step": NVAR * field_bytes, "steps": args.e2e_steps,
@@ -407,7 +415,7 @@ def main():
                              "whole_step_frac": value / world * BYTES_PER_CELL_UPDATE / 1e9 / peak}}
         if not args.no_cpu_baseline:
             try:
-                v, cores, kind, desc = cpu_reference_run(2, 1)
+                v, cores, kind, desc = cpu_reference_run(4, 1)
                 line["cpu_baseline"] = {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": kind, "sample": desc}
             except Exception as e:                                  # the baseline is a report, never a reason to fail
                 line["cpu_baseline"] = {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "unavailable",
