@@ -4,6 +4,7 @@
 #include "dycore_kernels.cuh"
 #include "stage_ws.cuh"
 #include "stage_uj.cuh"
+#include "stage_cell.cuh"
 #include "comm.cuh"
 #include <cmath>
 #include <algorithm>
@@ -83,34 +84,33 @@ template <int NT, int VAR> struct Tile {
   static constexpr int X = VAR == 1 ? 16 : ((NT <= 1) ? 32 : 24), Y = 8, MINB = VAR == 1 ? 2 : 1;
 };
 // Variant 2: warp-specialised kernel (stage_ws.cuh), 16 x 8 tile, reconstruction and update warps run concurrently.
+// Read once per handle (mw_dycore_create), so that tests can switch variants inside one process.
 static int tile_variant(int nt) {
-  static int v = -2;
-  if (v == -2) {
-    const char *e = getenv("MW_TILE_VARIANT");
-    v = e ? atoi(e) : -1;                              // -1 = default choice per tracer count (below)
-    const char *t = getenv("MW_NO_TMA");
-    if (t && atoi(t) != 0) v = 0;                           // the plain-load path exists in the phase kernel only
-  }
+  const char *e = getenv("MW_TILE_VARIANT");
+  int v = e ? atoi(e) : -1;                                // -1 = default choice (below)
+  const char *t = getenv("MW_NO_TMA");
+  if (t && atoi(t) != 0) v = 0;                            // the plain-load path exists in the phase kernel only
   // default: the warp-specialised kernel; with <= 1 tracer its segment form (x/y reconstructions as sliding line segments)
   // is 1.8 % faster, with 3 tracers 1 % slower (profiles/r01n_stage_seg_variant_ncu_summary.txt)
-  if (v == -1) return nt <= 1 ? 4 : (nt <= 3 ? 2 : 0);
+  if (v == -1 || v == 5) return 5;                         // cell kernel (stage_cell.cuh), every tracer count
   if (v == 4) return nt <= 3 ? 4 : 0;                    // ws kernel with segment reconstructions
   if (v == 3) return nt <= 1 ? 3 : (nt <= 3 ? 2 : 0);    // uniform-jobs kernel (stage_uj.cuh) where it fits in smem
   if (v == 2) return nt <= 3 ? 2 : 0;
   return (nt <= 1) ? v : 0;
 }
-static int tile_x(int nt) { return tile_variant(nt) >= 1 ? 16 : (nt <= 1 ? 32 : 24); }
-static int tile_y(int) { return 8; }
+static int tile_x_of(int v, int nt) { return v == 5 ? 32 : (v >= 1 ? 16 : (nt <= 1 ? 32 : 24)); }
 
 struct mw_dycore {
   mw_config cfg;
   int N;
+  int variant = 5, tile_x = 32;        // stage kernel variant and its tile width, fixed at creation (tile height is 8)
   double dx, dy, dz;
   int pitch;
   long long zstride, vstride;
   size_t qbytes;
   double *q[3] = {nullptr, nullptr, nullptr};
   CUtensorMap tmap[3];
+  CUtensorMap tmapI[3];                // cell kernel: interior box {32, 8, 1, N} of the same buffers (z windows)
   double *flux_x = nullptr, *flux_y = nullptr, *flux_z = nullptr, *mult = nullptr;
   double *bg = nullptr;                // hyc[nz], hytc[nz], hye[nz+1], hyte[nz+1]
   std::vector<double> bg_host;
@@ -218,6 +218,8 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   h->qbytes = (size_t) h->N * h->vstride * sizeof(double);
   const char *e = getenv("MW_NO_TMA");
   h->use_tma = (e && atoi(e) != 0) ? 0 : 1;
+  h->variant = tile_variant(cfg->num_tracers);
+  h->tile_x = tile_x_of(h->variant, cfg->num_tracers);
   const char *pe = getenv("MW_STAGE_PROF");
   if (pe && atoi(pe) != 0 && cudaMallocManaged(&h->prof, 8 * sizeof(unsigned long long)) == cudaSuccess) memset(h->prof, 0, 64);
   const int T = cfg->num_tracers > 0 ? cfg->num_tracers : 1;
@@ -240,8 +242,11 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   for (int b = 0; b < 3; ++b) {
     const uint64_t dims[4] = {(uint64_t) h->pitch, (uint64_t) (cfg->ny + 2 * HALO), (uint64_t) cfg->nz, (uint64_t) h->N};
     const uint64_t str[3] = {(uint64_t) h->pitch * 8, (uint64_t) h->zstride * 8, (uint64_t) h->vstride * 8};
-    const uint32_t box[4] = {(uint32_t) tile_x(cfg->num_tracers) + 2 * HALO, (uint32_t) tile_y(cfg->num_tracers) + 2 * HALO, 1, (uint32_t) h->N};
+    const uint32_t box[4] = {(uint32_t) h->tile_x + 2 * HALO, 8 + 2 * HALO, 1, (uint32_t) h->N};
     rc = encode_tensor_map_f64_4d(&h->tmap[b], h->q[b], dims, str, box);
+    if (rc != MW_OK) { mw_dycore_destroy(h); return rc; }
+    const uint32_t boxi[4] = {32, 8, 1, (uint32_t) h->N};
+    rc = encode_tensor_map_f64_4d(&h->tmapI[b], h->q[b], dims, str, boxi);
     if (rc != MW_OK) { mw_dycore_destroy(h); return rc; }
   }
   *out = h;
@@ -477,19 +482,28 @@ static int exchange_halos_async(mw_dycore *h, double *q, cudaStream_t st) {
 }
 // KIND 2: warp-specialised kernel with register z windows (stage_ws.cuh); KIND 3: uniform-jobs kernel (stage_uj.cuh)
 template <int NT, int KIND> struct WsKernel;
+template <int NT> struct WsKernel<NT, 5> {                       // cell kernel (stage_cell.cuh): 32 x 8 tile, one thread per cell
+  using C = CellCfg<NT>;
+  static constexpr int TX = 32;
+  static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P) { k_stage_cell<NT><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P); }
+  static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_cell<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
+};
 template <int NT> struct WsKernel<NT, 2> {
   using C = WsCfg<NT, 16, 8>;
-  static void launch(dim3 g, cudaStream_t st, const CUtensorMap &m, const StageParams &P) { k_stage_ws<NT, 16, 8><<<g, C::NTHR, C::SMEM, st>>>(m, P); }
+  static constexpr int TX = 16;
+  static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P) { k_stage_ws<NT, 16, 8><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], P); }
   static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_ws<NT, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
 };
 template <int NT> struct WsKernel<NT, 4> {                       // ws kernel with segment reconstructions (SEG = true)
   using C = WsCfg<NT, 16, 8>;
-  static void launch(dim3 g, cudaStream_t st, const CUtensorMap &m, const StageParams &P) { k_stage_ws<NT, 16, 8, true><<<g, C::NTHR, C::SMEM, st>>>(m, P); }
+  static constexpr int TX = 16;
+  static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P) { k_stage_ws<NT, 16, 8, true><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], P); }
   static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_ws<NT, 16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
 };
 template <int NT> struct WsKernel<NT, 3> {
   using C = UjCfg<NT, 16, 8>;
-  static void launch(dim3 g, cudaStream_t st, const CUtensorMap &m, const StageParams &P) { k_stage_uj<NT, 16, 8><<<g, C::NTHR, C::SMEM, st>>>(m, P); }
+  static constexpr int TX = 16;
+  static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P) { k_stage_uj<NT, 16, 8><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], P); }
   static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_uj<NT, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
 };
 template <int NT, int KIND = 2>
@@ -501,33 +515,34 @@ static int launch_stage_ws(mw_dycore *h, const StageParams &P0, int in_buf, cuda
     attr_set = true;
   }
   StageParams P = P0;
-  const int nbx = (P.nx + 15) / 16, nby = (P.ny + 7) / 8;
+  constexpr int TX = K::TX;
+  const int nbx = (P.nx + TX - 1) / TX, nby = (P.ny + 7) / 8;
   if (h->timing) {
     while (h->ev.size() < (size_t) (4 + 2 * h->n_stage_timed)) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
     cudaEventRecord(h->ev[2 + 2 * h->n_stage_timed], st);
   }
   if (!h->overlap) {
-    K::launch(dim3(nbx, nby), st, h->tmap[in_buf], P);
+    K::launch(dim3(nbx, nby), st, h, in_buf, P);
     h->launches++;
   } else {
     // Tiles whose stencil reaches a halo filled by a neighbour rank wait for the exchange; the others ("interior")
     // run while it is in flight.  Both sets are launched as concurrent kernels (second compute stream) so that the
     // small boundary launch fills SMs next to the interior launch instead of adding a wave of its own.
     P.nbx = nbx; P.nby = nby;
-    P.tbx_lo = h->dir_active[0] ? 1 : 0; P.tbx_hi = h->dir_active[0] ? std::max((P.nx - HALO) / 16, 0) : nbx;
+    P.tbx_lo = h->dir_active[0] ? 1 : 0; P.tbx_hi = h->dir_active[0] ? std::max((P.nx - HALO) / TX, 0) : nbx;
     P.tby_lo = h->dir_active[2] ? 1 : 0; P.tby_hi = h->dir_active[2] ? std::max((P.ny - HALO) / 8, 0) : nby;
     int n_int = (P.tbx_hi > P.tbx_lo && P.tby_hi > P.tby_lo) ? (P.tbx_hi - P.tbx_lo) * (P.tby_hi - P.tby_lo) : 0;
     if (n_int == 0) { P.tbx_lo = P.tbx_hi = 0; P.tby_lo = nby; P.tby_hi = nby; }   // everything is boundary ("low" rows)
     MW_CUDA_OK(cudaEventRecord(h->ev_prev, st));
     if (n_int > 0) {
       P.tile_mode = 1;
-      K::launch(dim3(n_int), st, h->tmap[in_buf], P);
+      K::launch(dim3(n_int), st, h, in_buf, P);
       h->launches++;
     }
     MW_CUDA_OK(cudaStreamWaitEvent(h->cs2, h->ev_prev, 0));
     if (h->halo_inflight) { MW_CUDA_OK(cudaStreamWaitEvent(h->cs2, h->ev_halo, 0)); h->halo_inflight = false; }
     P.tile_mode = 2;
-    K::launch(dim3(nbx * nby - n_int), h->cs2, h->tmap[in_buf], P);
+    K::launch(dim3(nbx * nby - n_int), h->cs2, h, in_buf, P);
     h->launches++;
     // the boundary cells' FCT factors go to the neighbours as soon as the boundary tiles are done (also overlapped)
     if (NT > 0) { int rc = exchange_mult(h, h->cs2); if (rc != MW_OK) return rc; }
@@ -543,10 +558,11 @@ static int launch_stage_ws(mw_dycore *h, const StageParams &P0, int in_buf, cuda
 }
 template <int NT>
 static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st, bool last) {
-  if constexpr (NT <= 1) { if (tile_variant(NT) == 3) return launch_stage_ws<NT, 3>(h, P, in_buf, st, last); }
-  if constexpr (NT <= 3) { if (tile_variant(NT) == 4) return launch_stage_ws<NT, 4>(h, P, in_buf, st, last); }
-  if constexpr (NT <= 3) { if (tile_variant(NT) == 2) return launch_stage_ws<NT, 2>(h, P, in_buf, st, last); }
-  if constexpr (NT <= 1) { if (tile_variant(NT) == 1) return launch_stage_v<NT, 1>(h, P, in_buf, st); }
+  if (h->variant == 5) return launch_stage_ws<NT, 5>(h, P, in_buf, st, last);
+  if constexpr (NT <= 1) { if (h->variant == 3) return launch_stage_ws<NT, 3>(h, P, in_buf, st, last); }
+  if constexpr (NT <= 3) { if (h->variant == 4) return launch_stage_ws<NT, 4>(h, P, in_buf, st, last); }
+  if constexpr (NT <= 3) { if (h->variant == 2) return launch_stage_ws<NT, 2>(h, P, in_buf, st, last); }
+  if constexpr (NT <= 1) { if (h->variant == 1) return launch_stage_v<NT, 1>(h, P, in_buf, st); }
   return launch_stage_v<NT, 0>(h, P, in_buf, st);
 }
 
@@ -706,7 +722,7 @@ static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double 
   const mw_config &c = h->cfg;
   static bool attr_set = false;
   if (!attr_set) { MW_CUDA_OK(K::attr()); attr_set = true; }
-  const int nbx = (c.nx + 15) / 16, nby = (c.ny + 7) / 8;
+  const int nbx = (c.nx + K::TX - 1) / K::TX, nby = (c.ny + 7) / 8;
   // ---- the chain of operations and their schedule (host_pipeline_plan above) ----
   double dt_dyn = dt_phys / ncycles;                                       // DYC:104-108
   std::vector<PlanLink> chain;
@@ -795,10 +811,10 @@ static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double 
       if (lk.kind == 1 && tb > nby) {
         // seam: tile rows [ta, nby) and [0, tb - nby) = every tile outside the rectangle of rows [tb - nby, ta) (tile_mode 2)
         P.tile_mode = 2; P.nbx = nbx; P.nby = nby; P.tbx_lo = 0; P.tbx_hi = nbx; P.tby_lo = tb - nby; P.tby_hi = ta;
-        K::launch(dim3(nbx * (tb - ta)), cs, h->tmap[in_buf], P);
+        K::launch(dim3(nbx * (tb - ta)), cs, h, in_buf, P);
       } else if (lk.kind == 1) {
         P.tile_mode = 1; P.nbx = nbx; P.nby = nby; P.tbx_lo = 0; P.tbx_hi = nbx; P.tby_lo = ta; P.tby_hi = tb;
-        K::launch(dim3(nbx * (tb - ta)), cs, h->tmap[in_buf], P);
+        K::launch(dim3(nbx * (tb - ta)), cs, h, in_buf, P);
       } else {
         P.jr_lo = j0; P.jr_n = nj;
         k_tracer_update<NT><<<cgrid, 256, 0, cs>>>(P);
@@ -866,30 +882,32 @@ extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields
   // rows with about one wave of tiles (148 SMs, one CTA each) per slab launch.  MW_HOST_SLAB_ROWS overrides (0 = off).
   int rows_per_slab = 0;
   {
-    const int nbx = (c.nx + 15) / 16;
+    const int nbx = (c.nx + h->tile_x - 1) / h->tile_x;
     int tile_rows = std::max(1, 148 / nbx);
     rows_per_slab = 8 * tile_rows;
     const char *e = getenv("MW_HOST_SLAB_ROWS");
     if (e) rows_per_slab = (atoi(e) / 8) * 8;
   }
-  const int variant = tile_variant(c.num_tracers);
+  const int variant = h->variant;
   const int ncycles = (int) ceil(dt_phys / mw_dycore_compute_time_step(h));                 // DYC:104-108
   // decomposed runs: every rank must walk the same schedule, so the blocks must be equal
   const bool equal_blocks = c.nproc_x * c.nproc_y == 1 ||
                             (h->comm && c.nx_glob % c.nproc_x == 0 && c.ny_glob % c.nproc_y == 0 && c.nx == c.nx_glob / c.nproc_x && c.ny == c.ny_glob / c.nproc_y);
-  const bool pipelined = rows_per_slab >= 8 && equal_blocks && c.ny_glob > 1 && (variant == 2 || variant == 4) &&
+  const bool pipelined = rows_per_slab >= 8 && equal_blocks && c.ny_glob > 1 && (variant == 2 || variant == 4 || variant == 5) &&
                          c.ny / rows_per_slab >= 4;
   if (pipelined) {
     MW_CUDA_OK(cudaDeviceSynchronize());                  // the non-blocking streams do not order against earlier default-stream work
     int rc = 1;
 #define MW_HOST_PIPE(NT)                                                                                          \
-  rc = variant == 4 ? host_step_pipelined<NT, 4>(h, host_fields, dt_phys, rows_per_slab, ncycles)                 \
+  rc = variant == 5 ? host_step_pipelined<NT, 5>(h, host_fields, dt_phys, rows_per_slab, ncycles)                 \
+     : variant == 4 ? host_step_pipelined<NT, 4>(h, host_fields, dt_phys, rows_per_slab, ncycles)                 \
                     : host_step_pipelined<NT, 2>(h, host_fields, dt_phys, rows_per_slab, ncycles)
     switch (c.num_tracers) {
       case 0: MW_HOST_PIPE(0); break;
       case 1: MW_HOST_PIPE(1); break;
       case 2: MW_HOST_PIPE(2); break;
       case 3: MW_HOST_PIPE(3); break;
+      case 4: if (variant == 5) rc = host_step_pipelined<4, 5>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
     }
 #undef MW_HOST_PIPE
     if (rc != 1) return rc;                               // 1 = grid too small for the chain: unpipelined path below
@@ -919,7 +937,7 @@ extern "C" int mw_dycore_attach_comm(mw_dycore *h, mw_comm *comm) {
   h->dir_active[2] = h->dir_active[3] = (c.nproc_y > 1) && !sim2d;
   {
     const char *e = getenv("MW_NO_OVERLAP");
-    h->overlap = (h->dir_active[0] || h->dir_active[2]) && tile_variant(c.num_tracers) >= 2 && !(e && atoi(e) != 0);
+    h->overlap = (h->dir_active[0] || h->dir_active[2]) && h->variant >= 2 && !(e && atoi(e) != 0);
     if (h->overlap && !h->cs) {
       // high priority: the few boundary CTAs and the pack / NCCL / unpack kernels are dispatched ahead of the queued
       // interior CTAs as SMs free up, so they never form a tail of their own

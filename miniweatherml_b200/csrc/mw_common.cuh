@@ -149,6 +149,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Blocking wait on an mbarrier phase.  try_wait suspends the thread in hardware until the phase completes or the time hint
+// (ns) expires, so a waiting warp costs a handful of issue slots per hint period instead of polling -- issue slots are what
+// the reconstruction warps are short of.  A lost hand-off must fail loudly, not hang the GPU: trap after 4M wake-ups.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t a = smem_u32(bar), hint = 20000u;
+  for (int spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity), "r"(hint)
+        : "memory");
+    if (spin > (1 << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // generic-proxy writes/reads of a smem buffer must be ordered before the async proxy (TMA) overwrites it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -9,6 +9,9 @@
 #include <cmath>
 #include <cfloat>
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace mw {
 
@@ -22,27 +25,39 @@ struct KesslerParams {
   double *temp;
   const double *rho_dry;
   double *rho_v, *rho_c, *rho_r, *precl;
-  double *pk_scratch;            // [nz][ncol], used only when rainsplit > 1
   unsigned long long *dtmin_bits; // global min of the per-cell stable sedimentation step (as ordered bits)
   int *rainsplit;                // device scalar written by k_kessler_split
+  double *bnd;                   // [ceil(nz/KES_LPT)-1][ncol]: initial rho_r of the first level of chunks 1, 2, ...
 };
 
-__device__ __forceinline__ double kessler_velqr(double qr, double r, double rhalf) {
-  return 36.34 * pow(qr * r, 0.1364) * rhalf;                        // KW eq. 2.15, KES:260,331
+// x^y for x >= 0 from a logarithm that is shared between the powers of one argument: exp(y * log x).  log(0) = -inf
+// gives exp(-inf) = 0 = pow(0, y) for the positive exponents used here; a negative x gives NaN like pow().  Relative
+// error <= (|y log x| + 1) ulp, i.e. a few 1e-15 for the arguments of this scheme (tolerance of the path: 1e-9).
+__device__ __forceinline__ double pow_from_log(double logx, double y) { return exp(y * logx); }
+
+// terminal fall speed, KW eq. 2.15 (KES:260,331): 36.34 * (qr*r)^0.1364 * rhalf, from log(qr*r)
+__device__ __forceinline__ double kessler_velqr(double log_rq, double rhalf) {
+  return 36.34 * pow_from_log(log_rq, 0.1364) * rhalf;
 }
+
+constexpr int KES_LPT = 16;     // levels per thread of the rainsplit == 1 kernel (see k_kessler_single)
 
 // Pass 0: global minimum of the per-cell CFL limit of the sedimentation (KES:255-276). The reference reduces
 // with yakl::intrinsics::minval; positive doubles order like their bit patterns, so an integer atomicMin does it.
 __global__ void __launch_bounds__(256) k_kessler_dtmin(const KesslerParams K) {
-  const long long n = (long long) (K.nz - 1) * K.ncol;
+  const long long n = (long long) (K.nz - 1) * K.ncol, nall = (long long) K.nz * K.ncol;
   double m = DBL_MAX;
-  for (long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long) gridDim.x * blockDim.x) {
-    const long long i = c % K.ncol;
-    const double rho = K.rho_dry[c], rho0 = K.rho_dry[i];
-    const double qr = K.rho_r[c] / rho;
-    const double vel = kessler_velqr(qr, 0.001 * rho, sqrt(rho0 / rho));
-    const double d = (vel > 1.e-10) ? 0.8 * K.dz / vel : K.dt;      // z(k+1)-z(k) = dz
-    m = fmin(m, d);
+  for (long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x; c < nall; c += (long long) gridDim.x * blockDim.x) {
+    const long long i = c % K.ncol, k = c / K.ncol;
+    const double rr = K.rho_r[c];
+    if (k > 0 && k % KES_LPT == 0) K.bnd[(k / KES_LPT - 1) * K.ncol + i] = rr;   // see k_kessler_single
+    if (c < n) {                                                      // the top level does not enter (KES:262)
+      const double rho = K.rho_dry[c], rho0 = K.rho_dry[i];
+      const double qr = rr / rho;
+      const double vel = kessler_velqr(log(qr * (0.001 * rho)), sqrt(rho0 / rho));
+      const double d = (vel > 1.e-10) ? 0.8 * K.dz / vel : K.dt;      // z(k+1)-z(k) = dz
+      m = fmin(m, d);
+    }
   }
   for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMin(K.dtmin_bits, (unsigned long long) __double_as_longlong(m));
@@ -53,96 +68,153 @@ __global__ void k_kessler_split(const KesslerParams K) {
   *K.rainsplit = (int) ceil(K.dt / dt_max);                          // KES:279
 }
 
-// Main pass: one thread per column marches upward once per sedimentation sub-cycle. Level k+1 is read before
-// level k is updated, which is exactly the reference's "sed kernel, then adjustment kernel" ordering (KES:288-335).
-// Between sub-cycles the state lives in the coupler arrays as (theta, qv, qc, qr); the last pass converts back.
-__global__ void __launch_bounds__(128) k_kessler_main(const KesslerParams K) {
+// One cell through one sedimentation sub-cycle's adjustment (KES:304-328).  State (theta, qv, qc, qr) in and out;
+// r = 0.001 rho, pk the Exner function, pc = 3.8 / (pk^(cp/Rd) psl), lq = log(qr) of the incoming qr.
+__device__ __forceinline__ void kessler_adjust(double &theta, double &qv, double &qc, double &qr, double lq, double sed,
+                                               double r, double pk, double pc, double dt0, double lv, double cp) {
+  const double qrprod = qc - (qc - dt0 * fmax(0.001 * (qc - 0.001), 0.)) / (1 + dt0 * 2.2 * pow_from_log(lq, 0.875));
+  qc = fmax(qc - qrprod, 0.);
+  qr = fmax(qr + qrprod + sed, 0.);
+  const double tmp = pk * theta - 36.;
+  const double qvs = pc * exp(17.27 * (pk * theta - 273.) / tmp);
+  const double prod = (qv - qvs) / (1. + qvs * (4093. * lv / cp) / (tmp * tmp));
+  const double lrq = log(r * qr);
+  const double tmp1 = dt0 * (((1.6 + 124.9 * pow_from_log(lrq, 0.2046)) * pow_from_log(lrq, 0.525)) /
+                             (2550000. * pc / (3.8 * qvs) + 540000.)) *
+                      (fmax(qvs - qv, 0.) / (r * qvs));
+  const double tmp2 = fmax(-prod - qc, 0.);
+  const double ern = fmin(tmp1, fmin(tmp2, qr));
+  const double cond = fmax(prod, -qc);
+  theta = theta + lv / (cp * pk) * (cond - ern);
+  qv = fmax(qv - cond + ern, 0.);
+  qc = qc + cond;
+  qr = qr - ern;
+}
+
+// rainsplit == 1 (every shipped case, almost every step): a cell needs its own initial state and the initial
+// (rho, qr) of the cell above it, nothing else -- the sedimentation flux uses pre-update values (KES:288-299) -- so the
+// update is cell-parallel.  A thread takes KES_LPT consecutive levels of one column, bottom-up with a one-level
+// look-ahead (the fall speed of a level is shared by the two flux differences it enters; the level above is read
+// before it is overwritten); consecutive threads take consecutive columns (coalesced).  The one value a thread needs
+// from ANOTHER thread's cells -- rho_r of the first level of the chunk above, which that thread updates in place --
+// is saved by the dtmin pass (bnd[chunk][col], 1/KES_LPT of a field).
+__global__ void __launch_bounds__(256) k_kessler_single(const KesslerParams K) {
+  if (*K.rainsplit != 1) return;
+  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nc = K.ncol, i = t % nc;
+  const int nz = K.nz, kc = (int) (t / nc), k0 = kc * KES_LPT;
+  if (k0 >= nz) return;
+  const double dt0 = K.dt;
+  const double psl = K.p0 / 100, rhoqr = 1000., lv = 2.5e6, cp = K.cp_d, kappa = K.R_d / K.cp_d;
+  const double rho_sfc = K.rho_dry[i];
+  long long c = (long long) k0 * nc + i;
+  double rho1 = K.rho_dry[c], qr1 = K.rho_r[c] / rho1, r1 = 0.001 * rho1;
+  double vel1 = kessler_velqr(log(qr1 * r1), sqrt(rho_sfc / rho1));
+  if (k0 == 0) K.precl[i] = rho_sfc * qr1 * vel1 / rhoqr;            // KES:291, 332-334 with rainsplit = 1
+  const int k1 = min(k0 + KES_LPT, nz);
+  double tk = K.temp[c], rv = K.rho_v[c], rc = K.rho_c[c];
+#pragma unroll 1
+  for (int k = k0; k < k1; ++k) {
+    const double rho = rho1, r = r1, vel = vel1;
+    double qr = qr1;
+    // the level above (pre-update values) and the next level's own fields, issued before this level's arithmetic
+    double rho_n = 1.0, rr_n = 0.0, tk_n = 0.0, rv_n = 0.0, rc_n = 0.0;
+    if (k < nz - 1) {
+      rho_n = K.rho_dry[c + nc];
+      rr_n = (k + 1 < k1) ? K.rho_r[c + nc] : K.bnd[(long long) kc * nc + i];
+      if (k + 1 < k1) { tk_n = K.temp[c + nc]; rv_n = K.rho_v[c + nc]; rc_n = K.rho_c[c + nc]; }
+    }
+    double sed;
+    if (k < nz - 1) {
+      rho1 = rho_n;
+      qr1 = rr_n / rho1;
+      r1 = 0.001 * rho1;
+      vel1 = kessler_velqr(log(qr1 * r1), sqrt(rho_sfc / rho1));
+      sed = dt0 * (r1 * qr1 * vel1 - r * qr * vel) / (r * K.dz);     // KES:296-297
+    } else {
+      sed = -dt0 * qr * vel / (0.5 * K.dz);                          // KES:294
+    }
+    double qv = rv / rho, qc = rc / rho;                             // KES:136-144
+    const double pratio = (K.R_d * rho * tk + K.R_v * rv * tk) / K.p0;
+    const double pk = pow_from_log(log(pratio), kappa);
+    double theta = tk / pk;
+    const double pc = 3.8 / (pratio * psl);                          // KES:258: pk^(cp/Rd) is the pressure ratio itself
+    kessler_adjust(theta, qv, qc, qr, log(qr), sed, r, pk, pc, dt0, lv, cp);
+    K.rho_v[c] = qv * rho; K.rho_c[c] = qc * rho; K.rho_r[c] = qr * rho; K.temp[c] = theta * pk;   // KES:154-161
+    c += nc;
+    tk = tk_n; rv = rv_n; rc = rc_n;
+  }
+}
+
+// rainsplit > 1: one thread per column marches DOWNWARD once and takes every level through all sub-cycles before it
+// moves on.  Sub-cycle nt of level k needs (qr, fall speed) of level k+1 as they were at the START of sub-cycle nt
+// (the reference runs its sedimentation kernel over all cells before the adjustment kernel, KES:288-335); those are
+// recorded per sub-cycle while level k+1 is processed.  The state of a cell stays in registers across its sub-cycles,
+// so there is no per-cell scratch and every field is read and written exactly once whatever rainsplit is.
+constexpr int KES_MAX_SPLIT = 128;
+__global__ void __launch_bounds__(128) k_kessler_split_columns(const KesslerParams K) {
+  const int rainsplit = *K.rainsplit;
+  if (rainsplit == 1) return;
+  if (rainsplit > KES_MAX_SPLIT || rainsplit < 1) __trap();          // dt is > 128 sedimentation CFL steps: fail loudly
   const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K.ncol) return;
-  const int nz = K.nz, rainsplit = *K.rainsplit;
+  const int nz = K.nz;
   const long long nc = K.ncol;
   const double dt0 = K.dt / (double) rainsplit;
-  const double psl = K.p0 / 100, rhoqr = 1000., lv = 2.5e6, cp = K.cp_d, Rd = K.R_d;
+  const double psl = K.p0 / 100, rhoqr = 1000., lv = 2.5e6, cp = K.cp_d, kappa = K.R_d / K.cp_d;
   const double rho_sfc = K.rho_dry[i];
-  double precl = 0.0;
-  for (int nt = 0; nt < rainsplit; ++nt) {
-    const bool first = (nt == 0), last = (nt == rainsplit - 1);
-    // level-0 lookahead values
-    double rho1 = rho_sfc;
-    double qr1 = first ? K.rho_r[i] / rho1 : K.rho_r[i];
-    double r1 = 0.001 * rho1, rhalf1 = sqrt(rho_sfc / rho1);
-    double vel1 = kessler_velqr(qr1, r1, rhalf1);
-    precl += rho_sfc * qr1 * vel1 / rhoqr;                           // KES:291
-    for (int k = 0; k < nz; ++k) {
-      const long long c = (long long) k * nc + i;
-      const double rho = rho1, r = r1, rhalf = rhalf1, vel = vel1;
-      double qr = qr1;
-      double sed;
-      if (k < nz - 1) {
-        rho1 = K.rho_dry[c + nc];
-        qr1 = first ? K.rho_r[c + nc] / rho1 : K.rho_r[c + nc];
-        r1 = 0.001 * rho1;
-        rhalf1 = sqrt(rho_sfc / rho1);
-        vel1 = kessler_velqr(qr1, r1, rhalf1);
-        sed = dt0 * (r1 * qr1 * vel1 - r * qr * vel) / (r * K.dz);   // KES:296-297
-      } else {
-        sed = -dt0 * qr * vel / (0.5 * K.dz);                        // KES:294
-      }
-      double qv, qc, theta, pk;
-      if (first) {                                                   // KES:136-144
-        const double t = K.temp[c], rv = K.rho_v[c];
-        qv = rv / rho;
-        qc = K.rho_c[c] / rho;
-        const double pressure = K.R_d * rho * t + K.R_v * rv * t;
-        pk = pow(pressure / K.p0, K.R_d / K.cp_d);
-        theta = t / pk;
-        if (rainsplit > 1) K.pk_scratch[c] = pk;
-      } else {
-        theta = K.temp[c]; qv = K.rho_v[c]; qc = K.rho_c[c]; pk = K.pk_scratch[c];
-      }
-      const double pc = 3.8 / (pow(pk, cp / Rd) * psl);              // KES:258
-      // KES:304-328
-      const double qrprod = qc - (qc - dt0 * fmax(0.001 * (qc - 0.001), 0.)) / (1 + dt0 * 2.2 * pow(qr, 0.875));
-      qc = fmax(qc - qrprod, 0.);
-      qr = fmax(qr + qrprod + sed, 0.);
-      const double tmp = pk * theta - 36.;
-      const double qvs = pc * exp(17.27 * (pk * theta - 273.) / tmp);
-      const double prod = (qv - qvs) / (1. + qvs * (4093. * lv / cp) / (tmp * tmp));
-      const double rq = r * qr;
-      const double tmp1 = dt0 * (((1.6 + 124.9 * pow(rq, 0.2046)) * pow(rq, 0.525)) /
-                                 (2550000. * pc / (3.8 * qvs) + 540000.)) *
-                          (fmax(qvs - qv, 0.) / (r * qvs));
-      const double tmp2 = fmax(-prod - qc, 0.);
-      const double ern = fmin(tmp1, fmin(tmp2, qr));
-      const double cond = fmax(prod, -qc);
-      theta = theta + lv / (cp * pk) * (cond - ern);
-      qv = fmax(qv - cond + ern, 0.);
-      qc = qc + cond;
-      qr = qr - ern;
-      if (last) {                                                    // KES:154-161
-        K.rho_v[c] = qv * rho; K.rho_c[c] = qc * rho; K.rho_r[c] = qr * rho; K.temp[c] = theta * pk;
-      } else {
-        K.rho_v[c] = qv; K.rho_c[c] = qc; K.rho_r[c] = qr; K.temp[c] = theta;
-      }
+  double hq[KES_MAX_SPLIT], hv[KES_MAX_SPLIT];                         // level k+1 at the start of each sub-cycle
+  double precl = 0.0, r_up = 0.0;
+  for (int k = nz - 1; k >= 0; --k) {
+    const long long c = (long long) k * nc + i;
+    const double rho = K.rho_dry[c], r = 0.001 * rho, rhalf = sqrt(rho_sfc / rho);
+    const double tk = K.temp[c], rv = K.rho_v[c];
+    double qr = K.rho_r[c] / rho, qv = rv / rho, qc = K.rho_c[c] / rho;
+    const double pratio = (K.R_d * rho * tk + K.R_v * rv * tk) / K.p0;
+    const double pk = pow_from_log(log(pratio), kappa);
+    double theta = tk / pk;
+    const double pc = 3.8 / (pratio * psl);
+    for (int nt = 0; nt < rainsplit; ++nt) {
+      const double vel = kessler_velqr(log(qr * r), rhalf);
+      if (k == 0) precl += rho_sfc * qr * vel / rhoqr;               // KES:291
+      const double sed = (k < nz - 1) ? dt0 * (r_up * hq[nt] * hv[nt] - r * qr * vel) / (r * K.dz)
+                                      : -dt0 * qr * vel / (0.5 * K.dz);
+      hq[nt] = qr; hv[nt] = vel;                                     // what the level below reads in its sub-cycle nt
+      kessler_adjust(theta, qv, qc, qr, log(qr), sed, r, pk, pc, dt0, lv, cp);
     }
+    K.rho_v[c] = qv * rho; K.rho_c[c] = qc * rho; K.rho_r[c] = qr * rho; K.temp[c] = theta * pk;
+    r_up = r;
   }
   K.precl[i] = precl / (double) rainsplit;                           // KES:332-334
 }
 
-// persistent scratch shared by the calls (grown on demand, never freed before process exit)
+// Scratch of the physics entry points.  One context per (device, stream): calls on different devices or on different
+// streams never share a buffer (the entry points take an arbitrary stream; two calls on the SAME stream are ordered by
+// the stream itself).  Buffers grow on demand and live until process exit.
 struct Scratch {
   void *p = nullptr;
   size_t bytes = 0;
   int ensure(size_t need) {
     if (need <= bytes) return MW_OK;
     if (p) cudaFree(p);
+    p = nullptr;
     bytes = 0;
     MW_CUDA_OK(cudaMalloc(&p, need));
     bytes = need;
     return MW_OK;
   }
 };
-static Scratch g_small, g_pk, g_partial;
+struct PhysCtx { Scratch small, partial, sums, nudge, kbnd; };
+static std::mutex g_ctx_mutex;
+static std::map<std::pair<int, cudaStream_t>, PhysCtx *> g_ctx;
+static PhysCtx *phys_ctx(cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  PhysCtx *&c = g_ctx[std::make_pair(dev, st)];
+  if (!c) c = new PhysCtx();
+  return c;
+}
 
 }  // namespace mw
 using namespace mw;
@@ -156,20 +228,21 @@ extern "C" int mw_kessler_step(int nz, long long ncol, double dz, double dt, dou
   MW_REQUIRE(dt > 0, "kessler called with nonpositive dt");            // KES:243
   MW_REQUIRE(temp && rho_dry && rho_v && rho_c && rho_r && precl, "mw_kessler_step: null field");
   cudaStream_t st = (cudaStream_t) stream;
-  rc = g_small.ensure(64);
+  PhysCtx *ctx = phys_ctx(st);
+  rc = ctx->small.ensure(64);
   if (rc != MW_OK) return rc;
   KesslerParams K;
   K.nz = nz; K.ncol = ncol; K.dz = dz; K.dt = dt; K.R_d = R_d; K.R_v = R_v; K.cp_d = cp_d; K.p0 = p0;
   K.temp = temp; K.rho_dry = rho_dry; K.rho_v = rho_v; K.rho_c = rho_c; K.rho_r = rho_r; K.precl = precl;
-  K.dtmin_bits = (unsigned long long *) g_small.p;
-  K.rainsplit = (int *) ((char *) g_small.p + 16);
-  // the sub-cycle scratch is only touched when rainsplit > 1, but must exist before the launch
-  rc = g_pk.ensure((size_t) nz * ncol * 8);
+  K.dtmin_bits = (unsigned long long *) ctx->small.p;
+  K.rainsplit = (int *) ((char *) ctx->small.p + 16);
+  const int nchunk = (nz + KES_LPT - 1) / KES_LPT;
+  rc = ctx->kbnd.ensure((size_t) std::max(nchunk - 1, 1) * ncol * 8);
   if (rc != MW_OK) return rc;
-  K.pk_scratch = (double *) g_pk.p;
+  K.bnd = (double *) ctx->kbnd.p;
   const unsigned long long init = 0x7FEFFFFFFFFFFFFFull;               // DBL_MAX
   MW_CUDA_OK(cudaMemcpyAsync(K.dtmin_bits, &init, 8, cudaMemcpyHostToDevice, st));
-  const long long n = (long long) (nz - 1) * ncol;
+  const long long n = (long long) nz * ncol;
   const unsigned grid = (unsigned) std::min<long long>((n + 255) / 256, 148 * 16);
   k_kessler_dtmin<<<grid, 256, 0, st>>>(K);
   MW_CUDA_OK(cudaGetLastError());
@@ -178,7 +251,10 @@ extern "C" int mw_kessler_step(int nz, long long ncol, double dz, double dt, dou
     if (rc != MW_OK) return rc;
   }
   k_kessler_split<<<1, 1, 0, st>>>(K);
-  k_kessler_main<<<(unsigned) ((ncol + 127) / 128), 128, 0, st>>>(K);
+  // exactly one of the two does the work (both read the device-side rainsplit; the other returns at once)
+  const long long nthr = ncol * nchunk;
+  k_kessler_single<<<(unsigned) ((nthr + 255) / 256), 256, 0, st>>>(K);
+  k_kessler_split_columns<<<(unsigned) ((ncol + 127) / 128), 128, 0, st>>>(K);
   MW_CUDA_OK(cudaGetLastError());
   if (rainsplit_out) {
     MW_CUDA_OK(cudaMemcpyAsync(rainsplit_out, K.rainsplit, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -260,9 +336,10 @@ __global__ void k_plane_final(const PlaneSumParams S) {
 
 static int plane_sums(PlaneSumParams &S, cudaStream_t st) {
   S.nb = (int) std::min<long long>(64, (S.np + 2047) / 2048);
-  int rc = g_partial.ensure((size_t) S.nf * S.nlev * S.nb * 8);
+  Scratch &partial = phys_ctx(st)->partial;
+  int rc = partial.ensure((size_t) S.nf * S.nlev * S.nb * 8);
   if (rc != MW_OK) return rc;
-  S.partial = (double *) g_partial.p;
+  S.partial = (double *) partial.p;
   k_plane_partial<<<dim3(S.nb, S.nf * S.nlev), 256, 0, st>>>(S);
   k_plane_final<<<(S.nf * S.nlev + 127) / 128, 128, 0, st>>>(S);
   MW_CUDA_OK(cudaGetLastError());
@@ -321,7 +398,6 @@ k_perturb_thermal(double *temp, int nz, int ny, int nx, int i_beg, int j_beg, do
   const double rad = sqrt(xn * xn + yn * yn + zn * zn);
   if (rad < 1) temp[c] += 5 * pow(cos(M_PI * rad / 2), 2.);
 }
-static Scratch g_sums;
 }  // namespace mw
 
 extern "C" int mw_sponge_layer(int nfields, double *const *fields, int nz, int ny, int nx, long long nglob, double dz,
@@ -332,11 +408,12 @@ extern "C" int mw_sponge_layer(int nfields, double *const *fields, int nz, int n
   const int num_layers = 10;                                           // sponge_layer.h:20
   MW_REQUIRE(nz >= num_layers, "mw_sponge_layer: nz = %d < 10", nz);
   cudaStream_t st = (cudaStream_t) stream;
-  rc = g_sums.ensure((size_t) MAXF * 512 * 8);
+  Scratch &sums = phys_ctx(st)->sums;
+  rc = sums.ensure((size_t) MAXF * 512 * 8);
   if (rc != MW_OK) return rc;
   PlaneSumParams P;
   P.nf = nfields; P.nlev = num_layers; P.k0 = nz - 1; P.kstep = -1; P.np = (long long) ny * nx;
-  P.out = (double *) g_sums.p; P.skip_field = 3;                       // WFLD: w relaxes to zero (sponge_layer.h:22,49)
+  P.out = (double *) sums.p; P.skip_field = 3;                       // WFLD: w relaxes to zero (sponge_layer.h:22,49)
   for (int f = 0; f < nfields; ++f) P.f[f] = fields[f];
   rc = plane_sums(P, st);
   if (rc != MW_OK) return rc;
@@ -380,7 +457,7 @@ extern "C" int mw_nudge_to_column(double *const *f5, int nz, int ny, int nx, lon
   if (rc != MW_OK) return rc;
   MW_REQUIRE(f5 && column, "mw_nudge_to_column: null argument");
   cudaStream_t st = (cudaStream_t) stream;
-  static Scratch sums;
+  Scratch &sums = phys_ctx(st)->nudge;
   rc = sums.ensure((size_t) 5 * nz * 8);
   if (rc != MW_OK) return rc;
   rc = column_sums(f5, nz, ny, nx, (double *) sums.p, comm, st);

@@ -1,0 +1,414 @@
+// The fused SSPRK3 stage kernel, one thread per cell ("cell kernel").  Same inputs, outputs and arithmetic as the
+// reference's compute_tendencies + RK combination (model/modules/dynamics_euler_stratified_wenofv.h:204-552, :119-174).
+//
+// Why this shape.  On B200 a warp-wide FP64 instruction holds a sub-partition's issue port for two cycles and nothing
+// else issues next to it (tools/issue_probe.cu), so a stage costs 2*F + O issue cycles (F fp64, O other instructions).
+// F is fixed by the algorithm (18 WENO5 reconstructions per cell and stage); the round-1 kernels spent O = 2100 on
+// descriptor decoding, shared-memory hand-offs between reconstruction and flux warps, register-window shifts, loop
+// control and barrier polling.  Here one thread owns one cell of a 32 x 8 tile and ALL variables of it, so that
+//   * every stencil load is one LDS with a compile-time offset from a per-thread base (x, y: the haloed plane of the
+//     level; z: a five-level window of interior planes in shared memory -- no register window, no shifts),
+//   * edge values, pressures and fluxes stay in registers: x neighbours trade them by warp shuffles (a warp is one
+//     tile row), z neighbours are the same thread one level later, only y neighbours go through shared memory,
+//   * there are no job tables, no inner loops and no role hand-offs: two CTA barriers per level.
+// The 1-cell ring of reconstructions around the tile (its outer faces need the far side's edge values) is dealt out as
+// single-variable jobs, two per thread and level.  Planes arrive by TMA: per level one haloed box {38, 14, 1, N} for
+// the x / y stencils (two slots) and one interior box {32, 8, 1, N} for the z windows (five slots).
+#pragma once
+#include "dycore_kernels.cuh"
+
+namespace mw {
+
+template <int NT>
+struct CellCfg {
+  static constexpr int N = NUM_STATE + NT, NV1 = N + 1;        // NV1: the variables plus the edge pressure
+  static constexpr int TX = 32, TY = 8, TT = TX * TY, NTHR = TT;
+  static constexpr int PX = TX + 2 * HALO, PY = TY + 2 * HALO, PLANE = PX * PY;
+  static constexpr int HSLOT = N * PLANE, HSLOTP = ((HSLOT + 15) / 16) * 16, NHS = 2;   // haloed planes (x / y stencils)
+  static constexpr int ISLOT = N * TT, NIS = 5;                                         // interior planes (z windows)
+  static constexpr int NRC = 2 * (TX + TY);                    // ring cells per variable and level
+  static constexpr int NRJ = N * NRC, NRND = (NRJ + NTHR - 1) / NTHR;
+  static constexpr int OFF_H = 0;
+  static constexpr int OFF_I = OFF_H + NHS * HSLOTP;
+  static constexpr int OFF_HY = OFF_I + NIS * ISLOT;           // [NV1][TY+1][TX] high-y edge values; row r = cell y = r-1
+  static constexpr int OFF_FY = OFF_HY + NV1 * (TY + 1) * TX;  // [N][TY+1][TX]   y face fluxes; row r = low face of cell y = r
+  static constexpr int OFF_RYL = OFF_FY + N * (TY + 1) * TX;   // [NV1][TX]       low-y edge values of the ring row y = TY
+  static constexpr int OFF_RXH = OFF_RYL + NV1 * TX;           // [NV1][TY]       high-x edge values of the ring column x = -1
+  static constexpr int OFF_RXL = OFF_RXH + NV1 * TY;           // [NV1][TY]       low-x edge values of the ring column x = TX
+  static constexpr int OFF_BAR = OFF_RXL + NV1 * TY;           // NHS + NIS mbarriers
+  static constexpr size_t SMEM = (size_t) (OFF_BAR + NHS + NIS) * 8;
+  static_assert(SMEM <= 227 * 1024, "cell kernel does not fit in shared memory");
+  static_assert(N * PLANE < (1 << 13), "ring descriptor field too narrow");
+  enum : unsigned { RJ_ISY = 1u << 13, RJ_HI = 1u << 14, RJ_IST = 1u << 15, RJ_VALID = 1u << 16 };
+};
+
+// Upwind face flux of all variables from the two face states (DYC:395-474).  L / R: edge values of (rho', u, v, w,
+// (rho theta)', c_tr) on the low / high side, pL / pR their pressures, hy_r / hy_t the hydrostatic density and rho*theta
+// added back at this face, IDN the normal velocity.  The rho*theta flux keeps the association the round-1 kernels
+// used (x, y: (m* / rho_up) * rt, z: (m* * rt) / rho_up) so results stay bit-identical with the plain-load kernel.
+template <int N, int IDN, bool ZDIR>
+__device__ __forceinline__ void face_flux(const double (&L)[N], const double (&R)[N], double pL, double pR, double hy_r,
+                                          double hy_t, double (&f)[N]) {
+  const double rL = L[idR] + hy_r, rR = R[idR] + hy_r;
+  const double mL = L[IDN] * rL, mR = R[IDN] * rR;
+  double m_upw, p_upw;
+  bool upL;
+  riemann(pL, pR, mL, mR, m_upw, p_upw, upL);
+  const double rinv = fast_rcp(upL ? rL : rR);
+  const double mth = m_upw * rinv;
+#pragma unroll
+  for (int l = 0; l < N; ++l) {
+    double v;
+    if (l == idR) v = m_upw;
+    else {
+      const double q_up = upL ? L[l] : R[l];
+      if (l == idT) v = ZDIR ? (m_upw * (q_up + hy_t)) * rinv : mth * (q_up + hy_t);
+      else v = m_upw * q_up;
+      if (l == IDN) v += p_upw;
+    }
+    f[l] = v;
+  }
+}
+
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+template <int NT>
+__global__ void __launch_bounds__(CellCfg<NT>::NTHR, 1)
+k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ CUtensorMap tmapI, const StageParams P) {
+  using C = CellCfg<NT>;
+  constexpr int N = C::N, TX = C::TX, TY = C::TY, TT = C::TT, PX = C::PX, PLANE = C::PLANE, NHS = C::NHS, NIS = C::NIS;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double *sm = reinterpret_cast<double *>(smem_raw);
+  uint64_t *hbar = reinterpret_cast<uint64_t *>(sm + C::OFF_BAR), *ibar = hbar + NHS;
+
+  const int tid = threadIdx.x, x = tid % TX, y = tid / TX;   // a warp is one tile row: lane = x
+  int tbx, tby;
+  tile_coords(P, tbx, tby);
+  const int i0 = tbx * TX, j0 = tby * TY, nz = P.nz;
+  const bool wall = (P.bc_z == MW_BC_WALL), sim2d = P.sim2d != 0;
+  const int gi = i0 + x, gj = j0 + y;
+  const bool in_dom = (gi < P.nx) && (gj < P.ny);
+  const long long plane_cells = (long long) P.ny * P.nx;
+
+  auto load_h = [&](int lev) {                               // haloed plane of level lev (thread 0 only)
+    fence_proxy_async();
+    mbar_expect_tx(&hbar[lev % NHS], (uint32_t) (C::HSLOT * 8));
+    tma_load_4d(sm + C::OFF_H + (lev % NHS) * C::HSLOTP, &tmapH, &hbar[lev % NHS], i0, j0, lev, 0);
+  };
+  auto load_i = [&](int lev) {                               // interior plane of level lev (thread 0 only)
+    fence_proxy_async();
+    mbar_expect_tx(&ibar[lev % NIS], (uint32_t) (C::ISLOT * 8));
+    tma_load_4d(sm + C::OFF_I + (lev % NIS) * C::ISLOT, &tmapI, &ibar[lev % NIS], i0 + HALO, j0 + HALO, lev, 0);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < NHS + NIS; ++s) mbar_init(&hbar[s], 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmapH);
+    tma_prefetch_desc(&tmapI);
+    for (int lev = 0; lev < 4 && lev < nz; ++lev) load_i(lev);
+    for (int lev = 0; lev < NHS && lev < nz; ++lev) load_h(lev);
+  }
+
+  // ---- my ring jobs (fixed for the whole kernel): job j = round * NTHR + tid; the (rho theta)' jobs come first so
+  // that the pressure evaluation is warp-uniform except in one warp.  A job reconstructs ONE variable of one ring cell
+  // and keeps the edge value that faces the tile.
+  unsigned rj[C::NRND];
+  int rj_dst[C::NRND], rj_pd[C::NRND];
+#pragma unroll
+  for (int r = 0; r < C::NRND; ++r) {
+    const int j = r * C::NTHR + tid;
+    bool valid = j < C::NRJ;
+    const int vs = valid ? j / C::NRC : 0, c = valid ? j % C::NRC : 0;
+    const int l = vs == 0 ? idT : (vs <= idT ? vs - 1 : vs);
+    int src, dst, pd;
+    unsigned fl = 0;
+    if (c < TY)               { src = (c + HALO) * PX;                     dst = C::OFF_RXH + l * TY + c;            pd = TY;            fl = C::RJ_HI; }
+    else if (c < 2 * TY)      { const int yy = c - TY;     src = (yy + HALO) * PX + TX + 1;      dst = C::OFF_RXL + l * TY + yy;  pd = TY; }
+    else if (c < 2 * TY + TX) { const int xx = c - 2 * TY; src = xx + HALO;                       dst = C::OFF_HY + l * (TY + 1) * TX + xx; pd = (TY + 1) * TX; fl = C::RJ_HI | C::RJ_ISY; }
+    else                      { const int xx = c - 2 * TY - TX; src = (TY + 1) * PX + xx + HALO;  dst = C::OFF_RYL + l * TX + xx;  pd = TX; fl = C::RJ_ISY; }
+    if ((fl & C::RJ_ISY) && sim2d) valid = false;
+    rj[r] = (unsigned) (l * PLANE + src) | fl | (l == idT ? C::RJ_IST : 0u) | (valid ? C::RJ_VALID : 0u);
+    rj_dst[r] = dst;
+    rj_pd[r] = pd * (N - idT);
+  }
+
+  // ---- running offsets ----------------------------------------------------------------------------------------------
+  long long hcell = (long long) (min(gj, P.ny - 1) + HALO) * P.pitch + (min(gi, P.nx - 1) + HALO);   // haloed arrays
+  long long gcell = (long long) min(gj, P.ny - 1) * P.nx + min(gi, P.nx - 1);                         // plain arrays
+  int img = 0;                                               // periodic images I write: bit0 +nx, bit1 -nx, bit2 +ny rows, bit3 -ny rows
+  if (P.wrap_x) img |= (gi < HALO ? 1 : 0) | (gi >= P.nx - HALO ? 2 : 0);
+  if (P.wrap_y) img |= (gj < HALO ? 4 : 0) | (gj >= P.ny - HALO ? 8 : 0);
+  if (!in_dom) img = 0;
+  const long long yimg = (long long) P.ny * P.pitch;
+  const bool have_q0 = P.rk_a != 0.0;
+  const int hoff = (y + HALO) * PX + (x + HALO);             // my cell in a haloed plane slot
+  double *HY = sm + C::OFF_HY, *FY = sm + C::OFF_FY;
+
+  // z window of variable v centred on level kc: levels kc-2 .. kc+2 from the interior planes, with the z boundary
+  // condition (DYC:752-781): copy the nearest interior level, a wall zeroes w
+  const double *Ibase = sm + C::OFF_I + tid;
+  auto zslot = [&](int lev) -> const double * {
+    const int lc = lev < 0 ? 0 : (lev >= nz ? nz - 1 : lev);
+    return Ibase + (lc % NIS) * C::ISLOT;
+  };
+  double hiz_prev[N], p_hiz_prev, fz_lo[N];
+  // z reconstruction of level kc -> lo / hi edge values and pressures (edge profiles kc and kc + 1)
+  auto zrecon = [&](int kc, double (&lo)[N], double (&hi)[N], double &p_lo, double &p_hi) {
+    const double *w0 = zslot(kc - 2), *w1 = zslot(kc - 1), *w2 = zslot(kc), *w3 = zslot(kc + 1), *w4 = zslot(kc + 2);
+    const bool z0 = wall && kc - 2 < 0, z1 = wall && kc - 1 < 0, z3 = wall && kc + 1 >= nz, z4 = wall && kc + 2 >= nz;
+#pragma unroll
+    for (int v = 0; v < N; ++v) {
+      double a0 = w0[v * TT], a1 = w1[v * TT], a2 = w2[v * TT], a3 = w3[v * TT], a4 = w4[v * TT];
+      if (v == idW) { if (z0) a0 = 0.0; if (z1) a1 = 0.0; if (z3) a3 = 0.0; if (z4) a4 = 0.0; }
+      weno5_edges(a0, a1, a2, a3, a4, lo[v], hi[v]);
+    }
+    p_lo = eos_pressure(lo[idT], __ldg(P.hyte + kc), __ldg(P.ihyte + kc), __ldg(P.pedge + kc), P);
+    p_hi = eos_pressure(hi[idT], __ldg(P.hyte + kc + 1), __ldg(P.ihyte + kc + 1), __ldg(P.pedge + kc + 1), P);
+  };
+  auto store_flux_z = [&](const double (&f)[N], long long gface) {
+    if (NT > 0 && in_dom) {
+#pragma unroll
+      for (int l = NUM_STATE; l < N; ++l) P.flux_z[(long long) (l - NUM_STATE) * (nz + 1) * plane_cells + gface] = f[l];
+    }
+  };
+
+  __syncthreads();                                           // barriers initialised
+
+  // ---- prologue: level 0 in z and the bottom boundary face (DYC:1020-1038: both sides mirrored, w = 0 at a wall) ----
+  for (int lev = 0; lev < 3 && lev < nz; ++lev) mbar_wait_spin(&ibar[lev % NIS], 0u);
+  {
+    double lo[N], hi[N], p_lo, p_hi;
+    zrecon(0, lo, hi, p_lo, p_hi);
+    double Lb[N];
+#pragma unroll
+    for (int v = 0; v < N; ++v) Lb[v] = (v == idW && wall) ? 0.0 : lo[v];
+    face_flux<N, idW, true>(Lb, Lb, p_lo, p_lo, __ldg(P.hye), __ldg(P.hyte), fz_lo);
+    store_flux_z(fz_lo, gcell);
+#pragma unroll
+    for (int v = 0; v < N; ++v) hiz_prev[v] = hi[v];
+    p_hiz_prev = p_hi;
+  }
+
+#pragma unroll 1
+  for (int k = 0; k < nz; ++k) {
+    const double *Hk = sm + C::OFF_H + (k % NHS) * C::HSLOTP;
+    const double hyc_k = __ldg(P.hyc + k), hytc_k = __ldg(P.hytc + k);
+    const double ihytc_k = __ldg(P.ihytc + k), pcell_k = __ldg(P.pcell + k);
+    // q0 of my cell: issued first, consumed after the second barrier
+    double q0v[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) q0v[l] = have_q0 ? P.q0[(long long) l * P.vstride + hcell] : 0.0;
+    double prop = 0.0;
+    if (P.use_immersed && in_dom) prop = __ldg(P.immersed + gcell);
+
+    mbar_wait_spin(&hbar[k % NHS], (uint32_t) ((k / NHS) & 1));
+    if (k + 3 < nz) mbar_wait_spin(&ibar[(k + 3) % NIS], (uint32_t) (((k + 3) / NIS) & 1));
+
+    // ================= phase 1: reconstructions =================
+    // ---- ring jobs ----
+#pragma unroll
+    for (int r = 0; r < C::NRND; ++r) {
+      const unsigned d = rj[r];
+      if (d & C::RJ_VALID) {
+        const double *q = Hk + (d & 0x1fffu);
+        const int st = (d & C::RJ_ISY) ? PX : 1;
+        double lo, hi;
+        weno5_edges(q[0], q[st], q[2 * st], q[3 * st], q[4 * st], lo, hi);
+        const double e = (d & C::RJ_HI) ? hi : lo;
+        sm[rj_dst[r]] = e;
+        if (d & C::RJ_IST) sm[rj_dst[r] + rj_pd[r]] = eos_pressure(e, hytc_k, ihytc_k, pcell_k, P);
+      }
+    }
+    // ---- y ----
+    const double *Hc = Hk + hoff;
+    double loy[N], hiy[N], p_loy = 0.0, p_hiy = 0.0;
+    if (!sim2d) {
+#pragma unroll
+      for (int v = 0; v < N; ++v) {
+        const double *q = Hc + v * PLANE;
+        weno5_edges(q[-2 * PX], q[-PX], q[0], q[PX], q[2 * PX], loy[v], hiy[v]);
+      }
+      p_loy = eos_pressure(loy[idT], hytc_k, ihytc_k, pcell_k, P);
+      p_hiy = eos_pressure(hiy[idT], hytc_k, ihytc_k, pcell_k, P);
+#pragma unroll
+      for (int v = 0; v < N; ++v) HY[(v * (TY + 1) + y + 1) * TX + x] = hiy[v];
+      HY[(N * (TY + 1) + y + 1) * TX + x] = p_hiy;
+    }
+    // ---- x ----
+    double lox[N], hix[N], p_lox, p_hix;
+#pragma unroll
+    for (int v = 0; v < N; ++v) {
+      const double *q = Hc + v * PLANE;
+      weno5_edges(q[-2], q[-1], q[0], q[1], q[2], lox[v], hix[v]);
+    }
+    p_lox = eos_pressure(lox[idT], hytc_k, ihytc_k, pcell_k, P);
+    p_hix = eos_pressure(hix[idT], hytc_k, ihytc_k, pcell_k, P);
+    // ---- z: level k+1 and the flux through face k+1/2 ----
+    double fz_hi[N];
+    {
+      const double he = __ldg(P.hye + k + 1), hte = __ldg(P.hyte + k + 1);
+      if (k + 1 < nz) {
+        double loz[N], hiz[N], p_loz, p_hiz;
+        zrecon(k + 1, loz, hiz, p_loz, p_hiz);
+        face_flux<N, idW, true>(hiz_prev, loz, p_hiz_prev, p_loz, he, hte, fz_hi);
+#pragma unroll
+        for (int v = 0; v < N; ++v) hiz_prev[v] = hiz[v];
+        p_hiz_prev = p_hiz;
+      } else {                                               // top boundary face
+        double Lt[N];
+#pragma unroll
+        for (int v = 0; v < N; ++v) Lt[v] = (v == idW && wall) ? 0.0 : hiz_prev[v];
+        face_flux<N, idW, true>(Lt, Lt, p_hiz_prev, p_hiz_prev, he, hte, fz_hi);
+      }
+      store_flux_z(fz_hi, gcell + plane_cells);
+    }
+    __syncthreads();                                         // A: ring + y edge values published; planes k (haloed) and k-1 (interior) dead
+    if (tid == 0) {
+      if (k + NHS < nz) load_h(k + NHS);
+      if (k + 4 < nz) load_i(k + 4);
+    }
+
+    // ================= phase 2: face fluxes =================
+    double tend[N];                                          // flux divergence, accumulated direction by direction
+    double fox_keep[NT > 0 ? NT : 1];                        // outgoing part of the tracers' x face fluxes (FCT)
+    {
+      double L[N], pL, f_lo[N], f_hi[N];
+#pragma unroll
+      for (int v = 0; v < N; ++v) L[v] = shfl_up1(hix[v]);
+      pL = shfl_up1(p_hix);
+      if (x == 0) {
+#pragma unroll
+        for (int v = 0; v < N; ++v) L[v] = sm[C::OFF_RXH + v * TY + y];
+        pL = sm[C::OFF_RXH + N * TY + y];
+      }
+      face_flux<N, idU, false>(L, lox, pL, p_lox, hyc_k, hytc_k, f_lo);
+#pragma unroll
+      for (int v = 0; v < N; ++v) f_hi[v] = shfl_dn1(f_lo[v]);
+      if (x == TX - 1) {
+        double R[N];
+#pragma unroll
+        for (int v = 0; v < N; ++v) R[v] = sm[C::OFF_RXL + v * TY + y];
+        face_flux<N, idU, false>(hix, R, p_hix, sm[C::OFF_RXL + N * TY + y], hyc_k, hytc_k, f_hi);
+      }
+      if (NT > 0 && gj < P.ny) {                             // tracer face fluxes for the FCT finish
+        const long long gx = ((long long) k * P.ny + gj) * (P.nx + 1) + gi;
+#pragma unroll
+        for (int l = NUM_STATE; l < N; ++l) {
+          double *fxg = P.flux_x + (long long) (l - NUM_STATE) * nz * ((long long) P.ny * (P.nx + 1)) + gx;
+          if (gi <= P.nx) fxg[0] = f_lo[l];
+          if (x == TX - 1 && gi + 1 <= P.nx) fxg[1] = f_hi[l];
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < N; ++v) tend[v] = -(f_hi[v] - f_lo[v]) * P.rdx;
+#pragma unroll
+      for (int l = NUM_STATE; l < N; ++l) fox_keep[l - NUM_STATE] = (fmax(f_hi[l], 0.0) - fmin(f_lo[l], 0.0)) * P.rdx;
+    }
+    double fy_lo[N];
+    if (!sim2d) {
+      double L[N], pL;
+#pragma unroll
+      for (int v = 0; v < N; ++v) L[v] = HY[(v * (TY + 1) + y) * TX + x];
+      pL = HY[(N * (TY + 1) + y) * TX + x];
+      face_flux<N, idV, false>(L, loy, pL, p_loy, hyc_k, hytc_k, fy_lo);
+#pragma unroll
+      for (int v = 0; v < N; ++v) FY[(v * (TY + 1) + y) * TX + x] = fy_lo[v];
+      double f_top[N];
+      if (y == TY - 1) {
+        double R[N];
+#pragma unroll
+        for (int v = 0; v < N; ++v) R[v] = sm[C::OFF_RYL + v * TX + x];
+        face_flux<N, idV, false>(hiy, R, p_hiy, sm[C::OFF_RYL + N * TX + x], hyc_k, hytc_k, f_top);
+#pragma unroll
+        for (int v = 0; v < N; ++v) FY[(v * (TY + 1) + TY) * TX + x] = f_top[v];
+      }
+      if (NT > 0 && gi < P.nx) {
+        const long long gy = ((long long) k * (P.ny + 1) + gj) * P.nx + gi;
+#pragma unroll
+        for (int l = NUM_STATE; l < N; ++l) {
+          double *fyg = P.flux_y + (long long) (l - NUM_STATE) * nz * ((long long) (P.ny + 1) * P.nx) + gy;
+          if (gj <= P.ny) fyg[0] = fy_lo[l];
+          if (y == TY - 1 && gj + 1 <= P.ny) fyg[P.nx] = f_top[l];
+        }
+      }
+    }
+    __syncthreads();                                         // B: y face fluxes published
+
+    // ================= tendencies, sources, RK combination, stores (DYC:519-551, 121-174) =================
+    {
+      double fy_hi[N];
+      if (!sim2d) {
+#pragma unroll
+        for (int v = 0; v < N; ++v) fy_hi[v] = FY[(v * (TY + 1) + y + 1) * TX + x];
+      }
+      const double *Ik = Ibase + (k % NIS) * C::ISLOT;      // my cell at level k
+      const double rho_k = Ik[idR * TT] + hyc_k;
+      const double u_k = Ik[idU * TT], v_k = Ik[idV * TT];
+      const double rho0 = q0v[idR] + hyc_k;
+      const double dtI = P.dt_stage, tau = 1.e3 * P.dt_stage;
+      const double imm_c = -fmin(1.0, dtI / tau) / dtI;      // immersed tendency = imm_c * q   (DYC:536-542)
+      double tR = tend[idR];
+      if (!sim2d) tR -= (fy_hi[idR] - fy_lo[idR]) * P.rdy;
+      tR -= (fz_hi[idR] - fz_lo[idR]) * P.rdz;
+      const double rhoP_k = rho_k - hyc_k;
+      if (P.use_immersed) tR = prop * (imm_c * rhoP_k) + (1.0 - prop) * tR;
+      const double rhoP_new = (P.rk_a * (rho0 - hyc_k) + P.rk_b * rhoP_k) + P.rk_cdt * tR;
+      const double r_new = fast_rcp(rhoP_new + hyc_k);
+      double *qo = P.qout + hcell;
+#pragma unroll
+      for (int l = 0; l < N; ++l, qo += P.vstride) {
+        if (in_dom) {
+          const double val_k = Ik[l * TT];
+          double t = tend[l];
+          if (!sim2d) t -= (fy_hi[l] - fy_lo[l]) * P.rdy;
+          t -= (fz_hi[l] - fz_lo[l]) * P.rdz;
+          double qc, q0c;                                    // conserved values of the stage input and of q0
+          if (l == idR || l == idT) { qc = val_k; q0c = q0v[l]; }
+          else { qc = val_k * rho_k; q0c = q0v[l] * rho0; }
+          if (l == idW && P.enable_gravity) t += -P.grav * rho_k;
+          if (l == idU) t += P.fcor * (v_k * rho_k);
+          if (l == idV) t -= P.fcor * (u_k * rho_k);
+          if (l == idV && sim2d) t = 0.0;
+          if (l < NUM_STATE) {
+            if (P.use_immersed) t = prop * (imm_c * qc) + (1.0 - prop) * t;
+            double out;
+            if (l == idR) out = rhoP_new;
+            else {
+              const double qn = (P.rk_a * q0c + P.rk_b * qc) + P.rk_cdt * t;
+              out = (l == idT) ? qn : qn * r_new;
+            }
+            qo[0] = out;
+            if (img) {
+              if (img & 1) qo[P.nx] = out;
+              if (img & 2) qo[-P.nx] = out;
+              if (img & 4) qo[yimg] = out;
+              if (img & 8) qo[-yimg] = out;
+            }
+          } else {
+            // tracer: leave the RK base value in qout and the FCT factor in mult for k_tracer_update
+            const int tr = l - NUM_STATE;
+            double m = 1.0;
+            if ((P.positive_mask >> tr) & 1u) {              // DYC:498-516
+              const double vol = P.dx * P.dy * P.dz;
+              const double mass_available = fmax(qc, 0.0) * vol;
+              const double fox = fox_keep[tr];
+              const double foy = sim2d ? 0.0 : (fmax(fy_hi[l], 0.0) - fmin(fy_lo[l], 0.0)) * P.rdy;
+              const double foz = (fmax(fz_hi[l], 0.0) - fmin(fz_lo[l], 0.0)) * P.rdz;
+              const double mass_out = (fox + foy + foz) * P.dt_stage * vol;
+              if (mass_out > mass_available) m = mass_available / mass_out;
+            }
+            P.mult[(long long) tr * nz * plane_cells + gcell] = m;
+            qo[0] = P.rk_a * q0c + P.rk_b * qc;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < N; ++l) fz_lo[l] = fz_hi[l];
+    gcell += plane_cells;
+    hcell += P.zstride;
+  }
+}
+
+}  // namespace mw

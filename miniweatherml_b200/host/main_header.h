@@ -5,7 +5,14 @@
 #pragma once
 #include "mw_b200.h"
 #include "mw_yaml.h"
+#include <cctype>
+#include <cerrno>
 #include <chrono>
+#include <ctime>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -49,6 +56,70 @@ struct Runtime {
     return dflt;
   }
 
+
+  // ---- ncclUniqueId rendezvous through a file -----------------------------------------------------------------------
+  // The file lives in a directory only this user can write (MW_RENDEZVOUS_DIR, else /tmp/mw_rdzv_<uid>, mode 0700,
+  // ownership checked, symlinks refused); its name carries the job's identity (MASTER_ADDR, MASTER_PORT, the launcher's
+  // run id and restart count), so concurrent jobs never share a name.  Rank 0 removes any leftover of a crashed run
+  // before it publishes (O_EXCL, mode 0600, write to a temporary name + rename); the payload is
+  // magic | publish time | id, and readers ignore a file published before their own start minus a launch skew, so a
+  // stale id is never picked up in the window before rank 0 gets to remove it.
+  std::string id_file;
+  static constexpr char const *ID_MAGIC = "MWNCCLID";
+  static long long now_s() { return (long long) ::time(nullptr); }
+  void exchange_nccl_id(unsigned char id[128]) {
+    char const *port = getenv("MASTER_PORT"), *dir_env = getenv("MW_RENDEZVOUS_DIR");
+    if (!(port && *port) && !(dir_env && *dir_env))
+      endrun("ERROR: a multi-rank run needs MASTER_PORT (torchrun sets it) or MW_RENDEZVOUS_DIR to name its NCCL id file");
+    std::string dir = (dir_env && *dir_env) ? dir_env : "/tmp/mw_rdzv_" + std::to_string((long long) ::getuid());
+    if (::mkdir(dir.c_str(), 0700) != 0 && errno != EEXIST) endrun("ERROR: cannot create rendezvous directory " + dir);
+    struct stat sd;
+    if (::lstat(dir.c_str(), &sd) != 0 || !S_ISDIR(sd.st_mode) || sd.st_uid != ::getuid() || (sd.st_mode & 022))
+      endrun("ERROR: rendezvous directory " + dir + " must be a real directory owned by this user and not group/world-writable");
+    auto env = [](char const *n) { char const *v = getenv(n); return std::string(v ? v : ""); };
+    std::string tag = env("MASTER_ADDR") + "_" + env("MASTER_PORT") + "_" + env("TORCHELASTIC_RUN_ID") + "_" +
+                      env("TORCHELASTIC_RESTART_COUNT") + "_" + env("MW_RENDEZVOUS_GEN") + "_n" + std::to_string(nranks);
+    for (char &ch : tag) if (!(isalnum((unsigned char) ch) || ch == '_' || ch == '-' || ch == '.')) ch = '-';
+    id_file = dir + "/nccl_id_" + tag;
+    const long long t_start = now_s();
+    long long skew = 120;                                  // ranks of one launch start within this many seconds
+    if (char const *v = getenv("MW_RENDEZVOUS_SKEW_S")) skew = atoll(v);
+    unsigned char buf[8 + 8 + 128];
+    if (rank == 0) {
+      ::unlink(id_file.c_str());                           // leftover of a run that died before its communicator existed
+      check(mw_comm_unique_id(id), "mw_comm_unique_id");
+      memcpy(buf, ID_MAGIC, 8);
+      memcpy(buf + 8, &t_start, 8);
+      memcpy(buf + 16, id, 128);
+      std::string tmp = id_file + ".tmp." + std::to_string((long long) ::getpid());
+      ::unlink(tmp.c_str());
+      int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+      if (fd < 0) endrun("ERROR: cannot create " + tmp);
+      const bool ok = ::write(fd, buf, sizeof(buf)) == (ssize_t) sizeof(buf);
+      ::close(fd);
+      if (!ok || ::rename(tmp.c_str(), id_file.c_str()) != 0) { ::unlink(tmp.c_str()); endrun("ERROR: cannot publish " + id_file); }
+      return;
+    }
+    double wait_s = 120;
+    if (char const *v = getenv("MW_RENDEZVOUS_TIMEOUT_S")) wait_s = atof(v);
+    for (int tries = 0; tries < (int) (wait_s * 100); ++tries) {
+      int fd = ::open(id_file.c_str(), O_RDONLY | O_NOFOLLOW);
+      if (fd >= 0) {
+        struct stat sf;
+        const bool mine = ::fstat(fd, &sf) == 0 && S_ISREG(sf.st_mode) && sf.st_uid == ::getuid();
+        const ssize_t n = mine ? ::read(fd, buf, sizeof(buf)) : -1;
+        ::close(fd);
+        long long t_pub = 0;
+        if (n == (ssize_t) sizeof(buf) && memcmp(buf, ID_MAGIC, 8) == 0) {
+          memcpy(&t_pub, buf + 8, 8);
+          if (t_pub >= t_start - skew) { memcpy(id, buf + 16, 128); return; }     // else: stale file, rank 0 will replace it
+        }
+      }
+      std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    }
+    endrun("ERROR: timed out waiting for a fresh NCCL id file " + id_file);
+  }
+
   void init() {
     if (initialised) return;
     rank       = env_int({"RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK"}, 0);
@@ -57,26 +128,10 @@ struct Runtime {
     check(mw_device_check(), "no usable B200 device (there is no CPU fallback)");
     check(mw_device_set(local_rank), "mw_device_set");
     if (nranks > 1) {
-      char const *dir = getenv("MW_RENDEZVOUS_DIR");
-      char const *port = getenv("MASTER_PORT");
-      std::string fn = std::string(dir ? dir : "/tmp") + "/mw_nccl_id_" + (port ? port : "0");
       unsigned char id[128];
-      if (rank == 0) {
-        check(mw_comm_unique_id(id), "mw_comm_unique_id");
-        std::string tmp = fn + ".tmp";
-        { std::ofstream f(tmp, std::ios::binary); f.write((char const *) id, 128); }
-        std::rename(tmp.c_str(), fn.c_str());
-      } else {
-        bool ok = false;
-        for (int tries = 0; tries < 6000 && !ok; ++tries) {          // up to 60 s
-          std::ifstream f(fn, std::ios::binary);
-          if (f && f.read((char *) id, 128) && f.gcount() == 128) ok = true;
-          else std::this_thread::sleep_for(std::chrono::milliseconds(10));
-        }
-        if (!ok) endrun("ERROR: timed out waiting for the NCCL id file " + fn);
-      }
+      exchange_nccl_id(id);
       check(mw_comm_create(id, nranks, rank, &comm), "mw_comm_create");
-      if (rank == 0) std::remove(fn.c_str());      // every rank holds the id once the communicator exists
+      if (rank == 0) ::unlink(id_file.c_str());    // every rank holds the id once the communicator exists
     }
     initialised = true;
   }
