@@ -33,8 +33,10 @@ ZLEN = 20000.0
 NUM_TRACERS = 1
 NVAR = 5 + NUM_TRACERS
 BYTES_PER_CELL_UPDATE = 64 * NVAR          # 8 N doubles per cell per SSPRK3 step
-CPU_SAMPLE = dict(nx=256, ny=256, nz=128)  # bounded sample of the same workload for the CPU arm: config 2's dz, dt and levels,
-                                           # a quarter of its columns (about 10 s of work for 16 host cores at 6 steps)
+CPU_SAMPLE = dict(nx=256, ny=256, nz=128)  # in-line cpu_baseline: config 2's dz, dt and levels, a quarter of its columns
+                                           # (about 10 s of work for 16 host cores)
+CPU_FULL = dict(nx=NX_LOC, ny=NY_LOC, nz=NZ)   # --impl reference: the whole per-GPU grid of the benchmark line
+REF_MAX_TIMED_STEPS = 4                    # ~6 s per step on 16 cores: 1 warm-up + 4 timed steps stay within two minutes
 
 
 def measured_peak():
@@ -99,6 +101,79 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "reasons": sorted(reasons)}
 
 
+NCU_METRICS = ["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+               "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "smsp__thread_inst_executed.sum",
+               "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+               "gpu__time_duration.sum"]
+
+
+def counters_child():
+    """Run by `ncu` from measure_counters(): two dycore steps of the benchmark workload on one GPU, nothing else."""
+    import torch
+    import miniweatherml_b200 as mw
+    from miniweatherml_b200.supercell import supercell_column
+    dev = torch.device("cuda", 0)
+    cfg = mw.make_config(NX_LOC, NY_LOC, NZ, NX_LOC * DX, NY_LOC * DX, ZLEN, NUM_TRACERS)
+    dy = mw.Dycore(cfg)
+    bg, col = supercell_column(NZ, ZLEN)
+    dy.set_background(bg)
+    names = ["density_dry", "uvel", "vvel", "wvel", "temp", "water_vapor"]
+    fields = [torch.tensor(col[n], device=dev)[:, None, None].expand(NZ, NY_LOC, NX_LOC).contiguous() for n in names]
+    mw.perturb_temperature(fields[4], 0, 0, DX, DX, ZLEN / NZ, NX_LOC * DX, NY_LOC * DX)
+    dt = dy.compute_time_step()
+    for _ in range(2):
+        dy.time_step(fields, dt)
+    torch.cuda.synchronize()
+    dy.close()
+
+
+def measure_counters(timeout_s=240):
+    """Instruction mix and DRAM traffic of the dominant kernel, counted on THIS box (outside the timed region): the
+    three stage launches of one step under `ncu --metrics ...` in a child process.  Returns a dict or {"error": ...}."""
+    import csv
+    import io
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return {"error": "ncu not found"}
+    cmd = [ncu, "--metrics", ",".join(NCU_METRICS), "--clock-control", "none", "-k", "regex:k_stage", "-s", "3", "-c", "3",
+           "--csv", sys.executable, os.path.abspath(__file__), "--counters-child"]
+    try:
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env).stdout
+    except Exception as e:
+        return {"error": "ncu child failed: %r" % (e,)}
+    rows = [r for r in csv.reader(io.StringIO(out)) if len(r) > 5]
+    hdr = next((r for r in rows if "Metric Name" in r), None)
+    if hdr is None:
+        return {"error": "no metrics in the ncu output: " + out[-300:].replace("\n", " ")}
+    iN, iV, iK, iI = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Kernel Name"), hdr.index("ID")
+    acc, ids, kern = {}, set(), None
+    for r in rows:
+        if r is hdr or len(r) <= max(iN, iV):
+            continue
+        try:
+            v = float(r[iV].replace(",", ""))
+        except ValueError:
+            continue
+        acc[r[iN]] = acc.get(r[iN], 0.0) + v
+        ids.add(r[iI]); kern = r[iK]
+    n = max(len(ids), 1)
+    if "smsp__thread_inst_executed.sum" not in acc:
+        return {"error": "metrics missing: " + ",".join(sorted(acc))}
+    cells = NX_LOC * NY_LOC * NZ
+    f64 = sum(acc.get(m, 0.0) for m in NCU_METRICS[:3])
+    return {"launches_counted": n, "kernel": kern.split("(")[0] if kern else None,
+            "fp64_thread_instr_per_cell_stage": f64 / n / cells,
+            "thread_instr_per_cell_stage": acc["smsp__thread_inst_executed.sum"] / n / cells,
+            "dram_bytes_per_launch": (acc.get("dram__bytes_read.sum", 0.0) + acc.get("dram__bytes_write.sum", 0.0)) / n,
+            "pipe_fp64_cycles_active_pct": acc.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) / n,
+            "ncu_kernel_ms_cold": acc.get("gpu__time_duration.sum", 0.0) / n / 1e6,
+            "source": "ncu --metrics (this run, this box), mean of the %d stage launches of one step" % n}
+
+
 def decomposition(nranks, rank):
     """The reference's x-y rank grid (model/core/coupler.h:127-179) for a 3-D run."""
     import math
@@ -119,21 +194,16 @@ def cpu_reference_run(steps, warmup, sample=CPU_SAMPLE):
     Returns (cell_updates_per_s, cores, kind, sample_description)."""
     ncores = os.cpu_count() or 1
     nx, ny, nz = sample["nx"], sample["ny"], sample["nz"]
-    desc = "dycore.time_step, supercell %dx%dx%d fp64 (config 2's dx=dy=1000 m, dz, dt and 128 levels; a quarter of its columns), %d steps" % (nx, ny, nz, steps)
+    frac = (nx * ny * nz) / float(NX_LOC * NY_LOC * NZ)
+    desc = "dycore.time_step, supercell %dx%dx%d fp64 (config 2's dx=dy=1000 m, dz, dt and 128 levels; %s of its per-GPU grid), %d timed steps after %d warm-up" % (
+        nx, ny, nz, "all" if frac == 1.0 else "%.3g" % frac, steps, warmup)
     exe = ref_driver(omp=True)
     if exe is not None:
         env = dict(os.environ, OMP_NUM_THREADS=str(ncores), GATOR_INITIAL_MB="4096")
-
-        def run(nsteps):
-            out = subprocess.run([exe, "run", "nx=%d" % nx, "ny=%d" % ny, "nz=%d" % nz, "xlen=%g" % (nx * DX),
-                                  "ylen=%g" % (ny * DX), "zlen=%g" % ZLEN, "tracers=vapor", "steps=%d" % nsteps, "time=1"],
-                                 env=env, capture_output=True, text=True, check=True).stdout
-            j = [json.loads(l) for l in out.splitlines() if l.startswith("{") and "seconds" in l][0]
-            return j["seconds"]
-        # the driver times its step loop only; warm-up = a separate short run that pages the binary in
-        if warmup > 0:
-            run(1)
-        sec = run(steps)
+        out = subprocess.run([exe, "run", "nx=%d" % nx, "ny=%d" % ny, "nz=%d" % nz, "xlen=%g" % (nx * DX),
+                              "ylen=%g" % (ny * DX), "zlen=%g" % ZLEN, "tracers=vapor", "steps=%d" % steps,
+                              "warmup=%d" % warmup, "time=1"], env=env, capture_output=True, text=True, check=True).stdout
+        sec = [json.loads(l) for l in out.splitlines() if l.startswith("{") and "seconds" in l][0]["seconds"]
         return nx * ny * nz * steps / sec, ncores, "reference", desc + " (oracle/_ref/ref_driver_omp, YAKL OpenMP backend, %d threads)" % ncores
     # no compiled reference on this box: the plain-C port, one core
     import numpy as np
@@ -166,17 +236,23 @@ def workload_config(world, dt=None):
 
 
 def run_reference_arm(args, rank):
+    """The reference's own CPU implementation on the box's host cores, on the benchmark line's per-GPU grid (the whole
+    512 x 512 x 128 block: at N = 1 that IS the configuration; at N > 1 the global grid is N such blocks and the CPU arm
+    times one of them, throughput-normalised).  Timed steps are capped so the run ends within a couple of minutes."""
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 6))
-    v, cores, kind, desc = cpu_reference_run(steps, min(args.warmup, 1))
+    steps = max(1, min(args.steps, REF_MAX_TIMED_STEPS))
+    warm = 1 if args.warmup > 0 else 0
+    t0 = time.time()
+    v, cores, kind, desc = cpu_reference_run(steps, warm, sample=CPU_FULL if ref_driver() else CPU_SAMPLE)
     line = {"impl": "reference", "metric": "cell-updates/s per SSPRK3 step", "value": v, "unit": "cell-updates/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "steps_timed": steps, "warmup_run": warm,
+            "ms_per_step": 1e3 * NX_LOC * NY_LOC * NZ / v if kind == "reference" else None,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(max(args.gpus, 1)), sample=desc),
+            "config": workload_config(max(args.gpus, 1)),
             "cpu_baseline": {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": v, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "wall_s": time.time() - t0}
     print(json.dumps(line), flush=True)
 
 
@@ -192,27 +268,49 @@ def run_config3(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    nxl = int(os.environ.get("MW_C3_NX", "1024")); nyl = int(os.environ.get("MW_C3_NY", "1024")); nz = NZ
+    nz = NZ
+    npx, npy, px, py = decomposition(world, rank)
+    if args.scaling == "strong":       # BASELINE configs[2] as written: ONE global 2048 x 2048 x 128 grid on 1/2/4/8 GPUs
+        nglob = int(os.environ.get("MW_C3_GLOB", "2048"))
+        assert nglob % npx == 0 and nglob % npy == 0
+        nxl, nyl = nglob // npx, nglob // npy
+    else:                              # weak form: 1024 x 1024 x 128 per GPU
+        nxl = int(os.environ.get("MW_C3_NX", "1024")); nyl = int(os.environ.get("MW_C3_NY", "1024"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         comm = mwd.create_comm(dist, rank, world, dev)
-    npx, npy, px, py = decomposition(world, rank)
     nxg, nyg = nxl * npx, nyl * npy
     T = 3
     cfg = mw.make_config(nxl, nyl, nz, nxg * DX, nyg * DX, ZLEN, T, nx_glob=nxg, ny_glob=nyg, i_beg=px * nxl,
                          j_beg=py * nyl, nproc_x=npx, nproc_y=npy, px=px, py=py)
-    dy = mw.Dycore(cfg)
-    if comm is not None:
-        dy.attach_comm(comm)
-    bg, col = supercell_column(nz, ZLEN)
-    dy.set_background(bg)
-    names = ["density_dry", "uvel", "vvel", "wvel", "temp", "water_vapor"]
-    fields = [torch.tensor(col[n], device=dev)[:, None, None].expand(nz, nyl, nxl).contiguous() for n in names]
-    fields += [torch.zeros((nz, nyl, nxl), device=dev, dtype=torch.float64) for _ in range(2)]
-    precl = torch.zeros((nyl, nxl), device=dev, dtype=torch.float64)
+    wl = {"workload": "BASELINE configs[2] (%s form): supercell + Kessler + sponge + nudging, N=8, %dx%dx%d fp64 per GPU"
+                      % (args.scaling, nxl, nyl, nz),
+          "global_grid": [nxg, nyg, nz], "decomposition": "%dx%d (x,y)" % (npx, npy)}
+    # device memory this needs per GPU: 3 RK registers of N haloed fields, 4 T tracer flux / FCT arrays, N coupler fields
+    need_gb = (3 * 8 * nz * (nyl + 6) * (nxl + 6) + (4 * T + 8) * nz * nyl * nxl) * 8 / 1e9
+    try:
+        dy = mw.Dycore(cfg)
+        if comm is not None:
+            dy.attach_comm(comm)
+        bg, col = supercell_column(nz, ZLEN)
+        dy.set_background(bg)
+        names = ["density_dry", "uvel", "vvel", "wvel", "temp", "water_vapor"]
+        fields = [torch.tensor(col[n], device=dev)[:, None, None].expand(nz, nyl, nxl).contiguous() for n in names]
+        fields += [torch.zeros((nz, nyl, nxl), device=dev, dtype=torch.float64) for _ in range(2)]
+        precl = torch.zeros((nyl, nxl), device=dev, dtype=torch.float64)
+    except (mw.MwError, torch.OutOfMemoryError) as e:
+        # the configuration does not fit this GPU count: say so instead of measuring something smaller
+        if rank == 0:
+            print(json.dumps({"report": "config3", "n_gpus": world, "scaling": args.scaling, "config": wl, "value": None,
+                              "oom": True, "needed_gb_per_gpu": need_gb,
+                              "hbm_gb": torch.cuda.get_device_properties(dev).total_memory / 1e9,
+                              "error": str(e)[:300]}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     f5 = [fields[0], fields[1], fields[2], fields[4], fields[5]]
     column = mw.column_average(f5, nxy_glob=nxg * nyg, comm=comm)
     mw.perturb_temperature(fields[4], px * nxl, py * nyl, DX, DX, ZLEN / nz, nxg * DX, nyg * DX)
@@ -256,11 +354,8 @@ def run_config3(args):
             "report": "config3", "metric": "cell-updates/s per SSPRK3 step", "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "value": full, "ms_per_step": ms / args.steps,
             "dycore_only_value": dyc, "dycore_ms_per_step": dyc_ms, "stage_kernel_ms": s_ms / max(s_n, 1),
-            "scaling": "weak", "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2] (weak form): supercell + Kessler + sponge + nudging, N=8, "
-                                   "%dx%dx%d fp64 per GPU" % (nxl, nyl, nz),
-                       "global_grid": [nxg, nyg, nz], "decomposition": "%dx%d (x,y)" % (npx, npy), "dt": dt,
-                       "state_finite": finite},
+            "scaling": args.scaling, "dtype": "f64", "data": "synthetic",
+            "config": dict(wl, dt=dt, state_finite=finite), "needed_gb_per_gpu": need_gb,
             "hbm_frac_full_step": full / world * bytes_full / 1e9 / peak,
             "hbm_frac_dycore": dyc / world * 64 * 8 / 1e9 / peak, "peak": peak, "peak_source": peak_src,
             "mem_gb": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
@@ -275,12 +370,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-counters", action="store_true", help="skip the ncu child that counts instructions / DRAM bytes")
+    ap.add_argument("--no-parity", action="store_true", help="skip the fixture parity check after the measurement")
+    ap.add_argument("--counters-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="config3 only: weak = 1024x1024x128 per GPU, strong = global 2048x2048x128 (BASELINE configs[2])")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
                     help="config2 (default, the contract line): dry dycore 512x512x128 per GPU; config3: supercell + Kessler "
                          "+ sponge + nudging (N=8), 1024x1024x128 per GPU (SURVEY 8(d) weak-scaling size), extra report line")
     args = ap.parse_args()
+    if args.counters_child:
+        return counters_child()
     if args.workload == "config3" and args.impl != "reference":
         return run_config3(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -370,6 +472,17 @@ def main():
         e2e_value = cells_glob * args.e2e_steps / e2e_s.item()
     field_bytes = NZ * NY_LOC * NX_LOC * 8
 
+    # ---- N-rank correctness against committed reference fixtures (untimed, every rank takes part) --------------------
+    parity = None
+    if not args.no_parity:
+        from miniweatherml_b200.parity import fixture_parity
+        parity = []
+        for name in ("box3d_vapor_dycore5.npz", "building_city_loop6.npz"):
+            try:
+                parity.append(fixture_parity(dist, comm, rank, world, dev, name))
+            except Exception as e:                                  # a failed check is reported, never hidden
+                parity.append({"fixture": name, "ok": False, "error": repr(e)})
+
     if rank == 0:
         peak, peak_src = measured_peak()
         cells_loc = NX_LOC * NY_LOC * NZ
@@ -378,36 +491,39 @@ def main():
         alg_bytes_per_launch = cells_loc * 8.0 * NVAR * 8.0 / 3.0
         k_ms = s_ms / max(s_n, 1)
         achieved = alg_bytes_per_launch / (k_ms * 1e-3) / 1e9
-        traffic = None
+        # instruction mix / DRAM traffic (ncu child) and the DFMA issue rate (probe kernel): both measured now, on this box
+        counters = {"error": "skipped (--no-counters)"} if (args.no_counters or world > 1) else measure_counters()
+        traffic = counters.get("dram_bytes_per_launch")
         fp64 = None
-        pj = os.path.join(ROOT, "profiles", "stage_kernel_bench.json")
-        if os.path.exists(pj):
-            try:
-                pr = json.load(open(pj))
-                traffic = pr.get("dram_bytes_per_launch")
-                # FP64-pipe view of the same launch: fp64 instructions per cell-stage counted by ncu (committed capture)
-                # x cells / live CUDA-event duration, against the DFMA issue rate measured by tools/fp64_peak.cu
-                fi = pr.get("fp64_thread_instr_per_cell_stage")
-                pk = pr.get("fp64_peak_thread_instr_per_s")
-                if fi and pk:
-                    ach = fi * cells_loc / (k_ms * 1e-3)
-                    fp64 = {"bound": "fp64-pipe", "achieved": ach / 1e12, "peak": pk / 1e12, "unit": "T fp64-instr/s",
-                            "frac": ach / pk, "fp64_instr_per_cell_stage": fi,
-                            "ncu_pipe_fp64_cycles_active_pct": pr.get("ncu_pipe_fp64_cycles_active_pct"),
-                            "peak_source": "measured DFMA issue rate (tools/fp64_peak.cu, profiles/r01a_device_peaks.jsonl)"}
-            except Exception:
-                pass
+        try:
+            pk = mw.probe_fp64_rate()
+            fi = counters.get("fp64_thread_instr_per_cell_stage")
+            fp64 = {"bound": "fp64-pipe", "peak": pk / 1e12, "unit": "T fp64-instr/s",
+                    "peak_source": "mw_probe_fp64_rate: DFMA issue rate measured in this run"}
+            if fi:
+                ach = fi * cells_loc / (k_ms * 1e-3)
+                fp64.update({"achieved": ach / 1e12, "frac": ach / pk, "fp64_instr_per_cell_stage": fi,
+                             "other_instr_per_cell_stage": counters["thread_instr_per_cell_stage"] - fi,
+                             "ncu_pipe_fp64_cycles_active_pct": counters.get("pipe_fp64_cycles_active_pct"),
+                             "counters_source": counters.get("source")})
+            else:
+                fp64["counters"] = counters.get("error")
+        except Exception as e:
+            fp64 = {"error": repr(e)}
         line = {"metric": "cell-updates/s per SSPRK3 step", "value": value, "unit": "cell-updates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": dict(workload_config(world, dt), state_finite=finite),
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": NVAR * field_bytes,
-                        "d2h_bytes_per_step": NVAR * field_bytes, "steps": args.e2e_steps,
-                        "api": "mw_dycore_time_step_host (pinned host buffers)"},
+                "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": world * NVAR * field_bytes,
+                        "d2h_bytes_per_step": world * NVAR * field_bytes, "bytes_are": "whole job (all ranks); per rank = /n_gpus",
+                        "steps": args.e2e_steps, "api": "mw_dycore_time_step_host (pinned host buffers)"},
                 "gpu_launches": int(launches),
+                "parity": None if parity is None else {"ok": all(p.get("ok") is not False for p in parity) and any(p.get("ok") for p in parity),
+                                                       "max_rel_err": max([p.get("max_rel_err", 0.0) for p in parity if p] or [None]),
+                                                       "tol": 1e-9, "checks": parity},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "k_stage_ws<1,16,8,SEG>", "kernel_ms": k_ms, "peak_source": peak_src,
+                             "traffic": traffic, "kernel": counters.get("kernel") or "k_stage_cell<1>", "kernel_ms": k_ms, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                              "note": "the fused stage kernel is FP64-pipe-bound, not HBM-bound (DESIGN.md section 4): "
                                      "the binding roofline is reported under fp64_pipe",

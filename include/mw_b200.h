@@ -84,6 +84,9 @@ int  mw_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);     
 int  mw_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);     /* synchronises the stream */
 int  mw_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
 int  mw_fence(void);                                                             /* yakl::fence() */
+/* measurement aid (no reference counterpart): DFMA thread-instructions per second this device sustains, the peak of
+ * the fp64_pipe roofline in bench.py */
+int  mw_probe_fp64_rate(double *dfma_thread_instr_per_s);
 
 /* ---- dycore ------------------------------------------------------------------------------------------- */
 int  mw_dycore_create(const mw_config *cfg, mw_dycore **out);
@@ -166,6 +169,9 @@ int  mw_mlp_dense2_forward(long long B, int nin, int nh, int nout, float negativ
                            const float *x, float *y, void *stream);
 
 /* ---- the other calls of the canonical step loop ---------------------------------------------------------- */
+/* the surrogate module's per-step diagnostic (PON:258-269: sum(a - b) / size of nfields field pairs), reduced on the device */
+int  mw_mean_difference(int nfields, const double *const *a, const double *const *b, long long n, double *mean_host,
+                        void *stream);
 int  mw_sponge_layer(int nfields, double *const *fields, int nz, int ny, int nx, long long nx_glob_ny_glob,
                      double dz, double zlen, double dt, double time_scale, mw_comm *comm, void *stream);
 /* column[5][nz] (device) <- horizontal mean of (density_dry,uvel,vvel,temp,water_vapor) */

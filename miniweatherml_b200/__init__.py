@@ -9,4 +9,4 @@ B200 every compute call raises.
 from .capi import (MwError, Config, Dycore, lib, lib_path, make_config, weno5_edges, kessler_step,  # noqa: F401
                    mlp_forward, surrogate_forward, sponge_layer, column_average, nudge_to_column,
                    perturb_temperature, city_layout, extract_column, horizontal_sponge_apply,
-                   time_average_accumulate, mlp_dense2_forward)
+                   time_average_accumulate, mlp_dense2_forward, mean_difference, probe_fp64_rate)

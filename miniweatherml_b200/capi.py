@@ -85,11 +85,20 @@ def lib():
         ("mw_comm_create", [vp, C.c_int, C.c_int, C.POINTER(vp)]),
         ("mw_comm_destroy", [vp]),
         ("mw_comm_barrier", [vp]),
+        ("mw_probe_fp64_rate", [dp]),
+        ("mw_mean_difference", [C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_longlong, dp, vp]),
     ]:
         if hasattr(L, name):
             getattr(L, name).argtypes = args
     _lib = L
     return L
+
+
+def probe_fp64_rate():
+    """DFMA thread-instructions per second of the current device (mw_probe_fp64_rate)."""
+    v = C.c_double(0.0)
+    _check(lib().mw_probe_fp64_rate(C.byref(v)))
+    return v.value
 
 
 def _check(rc):
@@ -334,6 +343,13 @@ def horizontal_sponge_apply(fields, column, dt, sponge_cells=10, time_scale=1.0,
     _check(lib().mw_horizontal_sponge_apply(len(fields), _ptr_array(fields), _ptr(column), nz, ny, nx, sponge_cells,
                                             time_scale, dt, int(x1), int(x2), int(y1), int(y2), px, nproc_x, py, nproc_y,
                                             _stream()))
+
+
+def mean_difference(a, b):
+    """[mean(a_f - b_f) for f]: the surrogate module's "Relative diff" diagnostic (PON:258-269), reduced on the device"""
+    out = (C.c_double * len(a))()
+    _check(lib().mw_mean_difference(len(a), _ptr_array(a), _ptr_array(b), a[0].numel(), out, _stream()))
+    return [out[i] for i in range(len(a))]
 
 
 def time_average_accumulate(avg, val, etime, dt):

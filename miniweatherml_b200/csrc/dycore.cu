@@ -245,7 +245,7 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
     const uint32_t box[4] = {(uint32_t) h->tile_x + 2 * HALO, 8 + 2 * HALO, 1, (uint32_t) h->N};
     rc = encode_tensor_map_f64_4d(&h->tmap[b], h->q[b], dims, str, box);
     if (rc != MW_OK) { mw_dycore_destroy(h); return rc; }
-    const uint32_t boxi[4] = {32, 8, 1, (uint32_t) h->N};
+    const uint32_t boxi[4] = {34, 8, 1, (uint32_t) h->N};   // CellCfg::IW x TY
     rc = encode_tensor_map_f64_4d(&h->tmapI[b], h->q[b], dims, str, boxi);
     if (rc != MW_OK) { mw_dycore_destroy(h); return rc; }
   }

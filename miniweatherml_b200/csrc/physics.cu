@@ -68,24 +68,30 @@ __global__ void k_kessler_split(const KesslerParams K) {
   *K.rainsplit = (int) ceil(K.dt / dt_max);                          // KES:279
 }
 
+// a / b with the ~1 ulp reciprocal of mw_common.cuh (MUFU seed + two Newton steps, no slow path): every divisor of this
+// scheme is a positive, normal number (densities, 1 + ..., (T - 36)^2, ...); IEEE division costs about four times as much
+__device__ __forceinline__ double qdiv(double a, double b) { return a * fast_rcp(b); }
+
 // One cell through one sedimentation sub-cycle's adjustment (KES:304-328).  State (theta, qv, qc, qr) in and out;
 // r = 0.001 rho, pk the Exner function, pc = 3.8 / (pk^(cp/Rd) psl), lq = log(qr) of the incoming qr.
 __device__ __forceinline__ void kessler_adjust(double &theta, double &qv, double &qc, double &qr, double lq, double sed,
                                                double r, double pk, double pc, double dt0, double lv, double cp) {
-  const double qrprod = qc - (qc - dt0 * fmax(0.001 * (qc - 0.001), 0.)) / (1 + dt0 * 2.2 * pow_from_log(lq, 0.875));
+  const double qrprod = qc - qdiv(qc - dt0 * fmax(0.001 * (qc - 0.001), 0.), 1 + dt0 * 2.2 * pow_from_log(lq, 0.875));
   qc = fmax(qc - qrprod, 0.);
   qr = fmax(qr + qrprod + sed, 0.);
   const double tmp = pk * theta - 36.;
-  const double qvs = pc * exp(17.27 * (pk * theta - 273.) / tmp);
-  const double prod = (qv - qvs) / (1. + qvs * (4093. * lv / cp) / (tmp * tmp));
+  const double itmp = fast_rcp(tmp);
+  const double qvs = pc * exp(17.27 * (pk * theta - 273.) * itmp);
+  const double iqvs = fast_rcp(qvs);
+  const double prod = qdiv(qv - qvs, 1. + qvs * (4093. * lv / cp) * (itmp * itmp));
   const double lrq = log(r * qr);
-  const double tmp1 = dt0 * (((1.6 + 124.9 * pow_from_log(lrq, 0.2046)) * pow_from_log(lrq, 0.525)) /
-                             (2550000. * pc / (3.8 * qvs) + 540000.)) *
-                      (fmax(qvs - qv, 0.) / (r * qvs));
+  const double tmp1 = dt0 * qdiv((1.6 + 124.9 * pow_from_log(lrq, 0.2046)) * pow_from_log(lrq, 0.525),
+                                 2550000. * pc * (iqvs * (1. / 3.8)) + 540000.) *
+                      (fmax(qvs - qv, 0.) * (fast_rcp(r) * iqvs));
   const double tmp2 = fmax(-prod - qc, 0.);
   const double ern = fmin(tmp1, fmin(tmp2, qr));
   const double cond = fmax(prod, -qc);
-  theta = theta + lv / (cp * pk) * (cond - ern);
+  theta = theta + qdiv(lv, cp * pk) * (cond - ern);
   qv = fmax(qv - cond + ern, 0.);
   qc = qc + cond;
   qr = qr - ern;
@@ -108,14 +114,15 @@ __global__ void __launch_bounds__(256) k_kessler_single(const KesslerParams K) {
   const double psl = K.p0 / 100, rhoqr = 1000., lv = 2.5e6, cp = K.cp_d, kappa = K.R_d / K.cp_d;
   const double rho_sfc = K.rho_dry[i];
   long long c = (long long) k0 * nc + i;
-  double rho1 = K.rho_dry[c], qr1 = K.rho_r[c] / rho1, r1 = 0.001 * rho1;
-  double vel1 = kessler_velqr(log(qr1 * r1), sqrt(rho_sfc / rho1));
+  double rho1 = K.rho_dry[c], irho1 = fast_rcp(rho1), qr1 = K.rho_r[c] * irho1, r1 = 0.001 * rho1;
+  double vel1 = kessler_velqr(log(qr1 * r1), sqrt(rho_sfc * irho1));
   if (k0 == 0) K.precl[i] = rho_sfc * qr1 * vel1 / rhoqr;            // KES:291, 332-334 with rainsplit = 1
+  const double idz = 1.0 / K.dz, ip0 = 1.0 / K.p0;
   const int k1 = min(k0 + KES_LPT, nz);
   double tk = K.temp[c], rv = K.rho_v[c], rc = K.rho_c[c];
 #pragma unroll 1
   for (int k = k0; k < k1; ++k) {
-    const double rho = rho1, r = r1, vel = vel1;
+    const double rho = rho1, irho = irho1, r = r1, vel = vel1;
     double qr = qr1;
     // the level above (pre-update values) and the next level's own fields, issued before this level's arithmetic
     double rho_n = 1.0, rr_n = 0.0, tk_n = 0.0, rv_n = 0.0, rc_n = 0.0;
@@ -127,18 +134,19 @@ __global__ void __launch_bounds__(256) k_kessler_single(const KesslerParams K) {
     double sed;
     if (k < nz - 1) {
       rho1 = rho_n;
-      qr1 = rr_n / rho1;
+      irho1 = fast_rcp(rho1);
+      qr1 = rr_n * irho1;
       r1 = 0.001 * rho1;
-      vel1 = kessler_velqr(log(qr1 * r1), sqrt(rho_sfc / rho1));
-      sed = dt0 * (r1 * qr1 * vel1 - r * qr * vel) / (r * K.dz);     // KES:296-297
+      vel1 = kessler_velqr(log(qr1 * r1), sqrt(rho_sfc * irho1));
+      sed = dt0 * (r1 * qr1 * vel1 - r * qr * vel) * (1000.0 * irho * idz);     // KES:296-297: / (r dz), r = 0.001 rho
     } else {
-      sed = -dt0 * qr * vel / (0.5 * K.dz);                          // KES:294
+      sed = -dt0 * qr * vel * (2.0 * idz);                           // KES:294
     }
-    double qv = rv / rho, qc = rc / rho;                             // KES:136-144
-    const double pratio = (K.R_d * rho * tk + K.R_v * rv * tk) / K.p0;
+    double qv = rv * irho, qc = rc * irho;                           // KES:136-144
+    const double pratio = (K.R_d * rho * tk + K.R_v * rv * tk) * ip0;
     const double pk = pow_from_log(log(pratio), kappa);
-    double theta = tk / pk;
-    const double pc = 3.8 / (pratio * psl);                          // KES:258: pk^(cp/Rd) is the pressure ratio itself
+    double theta = qdiv(tk, pk);
+    const double pc = qdiv(3.8, pratio * psl);                       // KES:258: pk^(cp/Rd) is the pressure ratio itself
     kessler_adjust(theta, qv, qc, qr, log(qr), sed, r, pk, pc, dt0, lv, cp);
     K.rho_v[c] = qv * rho; K.rho_c[c] = qc * rho; K.rho_r[c] = qr * rho; K.temp[c] = theta * pk;   // KES:154-161
     c += nc;
@@ -481,5 +489,62 @@ extern "C" int mw_perturb_temperature(double *temp, int nz, int ny, int nx, int 
   k_perturb_thermal<<<(unsigned) ((n + 255) / 256), 256, 0, (cudaStream_t) stream>>>(temp, nz, ny, nx, i_beg, j_beg, dx,
                                                                                   dy, dz, xlen, ylen);
   MW_CUDA_OK(cudaGetLastError());
+  return MW_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Mean difference of field pairs: the surrogate module's per-step diagnostic "Relative diff" (PON:258-269:
+// yakl::intrinsics::sum(a - b) / size), as one deterministic two-level reduction on the device; only nfields
+// doubles travel to the host.
+// ----------------------------------------------------------------------------------------------------------
+namespace mw {
+constexpr int MD_BLOCKS = 592;         // 4 per SM
+struct MeanDiffParams {
+  const double *a[MAXF], *b[MAXF];
+  long long n;
+  double *partial;                     // [nf][MD_BLOCKS]
+  double *out;                         // [nf]
+};
+__global__ void __launch_bounds__(256) k_diff_partial(const MeanDiffParams S) {
+  const int f = blockIdx.y;
+  __shared__ double red[8];
+  double s = 0.0;
+  const double *a = S.a[f], *b = S.b[f];
+  for (long long c = (long long) blockIdx.x * blockDim.x + threadIdx.x; c < S.n; c += (long long) gridDim.x * blockDim.x) s += a[c] - b[c];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    S.partial[f * MD_BLOCKS + blockIdx.x] = t;
+  }
+}
+__global__ void k_diff_final(const MeanDiffParams S, int nf) {
+  const int f = threadIdx.x;
+  if (f >= nf) return;
+  double t = 0.0;
+  for (int b = 0; b < MD_BLOCKS; ++b) t += S.partial[f * MD_BLOCKS + b];
+  S.out[f] = t / (double) S.n;
+}
+}  // namespace mw
+
+extern "C" int mw_mean_difference(int nfields, const double *const *a, const double *const *b, long long n,
+                                  double *mean_host, void *stream) {
+  int rc = device_check_cached();
+  if (rc != MW_OK) return rc;
+  MW_REQUIRE(nfields >= 1 && nfields <= MAXF && a && b && mean_host && n > 0, "mw_mean_difference: bad argument");
+  cudaStream_t st = (cudaStream_t) stream;
+  Scratch &partial = phys_ctx(st)->partial;
+  rc = partial.ensure((size_t) (MAXF * MD_BLOCKS + MAXF) * 8);
+  if (rc != MW_OK) return rc;
+  MeanDiffParams S;
+  for (int f = 0; f < nfields; ++f) { S.a[f] = a[f]; S.b[f] = b[f]; }
+  S.n = n; S.partial = (double *) partial.p; S.out = S.partial + MAXF * MD_BLOCKS;
+  k_diff_partial<<<dim3(MD_BLOCKS, nfields), 256, 0, st>>>(S);
+  k_diff_final<<<1, 32, 0, st>>>(S, nfields);
+  MW_CUDA_OK(cudaGetLastError());
+  MW_CUDA_OK(cudaMemcpyAsync(mean_host, S.out, nfields * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MW_CUDA_OK(cudaStreamSynchronize(st));
   return MW_OK;
 }

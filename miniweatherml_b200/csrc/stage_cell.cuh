@@ -25,7 +25,10 @@ struct CellCfg {
   static constexpr int TX = 32, TY = 8, TT = TX * TY, NTHR = TT;
   static constexpr int PX = TX + 2 * HALO, PY = TY + 2 * HALO, PLANE = PX * PY;
   static constexpr int HSLOT = N * PLANE, HSLOTP = ((HSLOT + 15) / 16) * 16, NHS = 2;   // haloed planes (x / y stencils)
-  static constexpr int ISLOT = N * TT, NIS = 5;                                         // interior planes (z windows)
+  // interior planes (z windows): rows of IW = TX + 2 cells starting one cell left of the tile, so that the box's first
+  // coordinate is a multiple of two doubles (TMA wants the start of a box row 16-byte aligned); cell x sits at x + IXO
+  static constexpr int IXO = 1, IW = TX + 2 * IXO, IPL = TY * IW;
+  static constexpr int ISLOT = N * IPL, NIS = 5;
   static constexpr int NRC = 2 * (TX + TY);                    // ring cells per variable and level
   static constexpr int NRJ = N * NRC, NRND = (NRJ + NTHR - 1) / NTHR;
   static constexpr int OFF_H = 0;
@@ -77,7 +80,7 @@ template <int NT>
 __global__ void __launch_bounds__(CellCfg<NT>::NTHR, 1)
 k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ CUtensorMap tmapI, const StageParams P) {
   using C = CellCfg<NT>;
-  constexpr int N = C::N, TX = C::TX, TY = C::TY, TT = C::TT, PX = C::PX, PLANE = C::PLANE, NHS = C::NHS, NIS = C::NIS;
+  constexpr int N = C::N, TX = C::TX, TY = C::TY, PX = C::PX, PLANE = C::PLANE, NHS = C::NHS, NIS = C::NIS, IPL = C::IPL;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double *sm = reinterpret_cast<double *>(smem_raw);
   uint64_t *hbar = reinterpret_cast<uint64_t *>(sm + C::OFF_BAR), *ibar = hbar + NHS;
@@ -99,7 +102,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
   auto load_i = [&](int lev) {                               // interior plane of level lev (thread 0 only)
     fence_proxy_async();
     mbar_expect_tx(&ibar[lev % NIS], (uint32_t) (C::ISLOT * 8));
-    tma_load_4d(sm + C::OFF_I + (lev % NIS) * C::ISLOT, &tmapI, &ibar[lev % NIS], i0 + HALO, j0 + HALO, lev, 0);
+    tma_load_4d(sm + C::OFF_I + (lev % NIS) * C::ISLOT, &tmapI, &ibar[lev % NIS], i0 + HALO - C::IXO, j0 + HALO, lev, 0);
   };
   if (tid == 0) {
     for (int s = 0; s < NHS + NIS; ++s) mbar_init(&hbar[s], 1);
@@ -147,7 +150,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
 
   // z window of variable v centred on level kc: levels kc-2 .. kc+2 from the interior planes, with the z boundary
   // condition (DYC:752-781): copy the nearest interior level, a wall zeroes w
-  const double *Ibase = sm + C::OFF_I + tid;
+  const double *Ibase = sm + C::OFF_I + y * C::IW + x + C::IXO;
   auto zslot = [&](int lev) -> const double * {
     const int lc = lev < 0 ? 0 : (lev >= nz ? nz - 1 : lev);
     return Ibase + (lc % NIS) * C::ISLOT;
@@ -159,7 +162,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     const bool z0 = wall && kc - 2 < 0, z1 = wall && kc - 1 < 0, z3 = wall && kc + 1 >= nz, z4 = wall && kc + 2 >= nz;
 #pragma unroll
     for (int v = 0; v < N; ++v) {
-      double a0 = w0[v * TT], a1 = w1[v * TT], a2 = w2[v * TT], a3 = w3[v * TT], a4 = w4[v * TT];
+      double a0 = w0[v * IPL], a1 = w1[v * IPL], a2 = w2[v * IPL], a3 = w3[v * IPL], a4 = w4[v * IPL];
       if (v == idW) { if (z0) a0 = 0.0; if (z1) a1 = 0.0; if (z3) a3 = 0.0; if (z4) a4 = 0.0; }
       weno5_edges(a0, a1, a2, a3, a4, lo[v], hi[v]);
     }
@@ -343,8 +346,8 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
         for (int v = 0; v < N; ++v) fy_hi[v] = FY[(v * (TY + 1) + y + 1) * TX + x];
       }
       const double *Ik = Ibase + (k % NIS) * C::ISLOT;      // my cell at level k
-      const double rho_k = Ik[idR * TT] + hyc_k;
-      const double u_k = Ik[idU * TT], v_k = Ik[idV * TT];
+      const double rho_k = Ik[idR * IPL] + hyc_k;
+      const double u_k = Ik[idU * IPL], v_k = Ik[idV * IPL];
       const double rho0 = q0v[idR] + hyc_k;
       const double dtI = P.dt_stage, tau = 1.e3 * P.dt_stage;
       const double imm_c = -fmin(1.0, dtI / tau) / dtI;      // immersed tendency = imm_c * q   (DYC:536-542)
@@ -359,7 +362,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
 #pragma unroll
       for (int l = 0; l < N; ++l, qo += P.vstride) {
         if (in_dom) {
-          const double val_k = Ik[l * TT];
+          const double val_k = Ik[l * IPL];
           double t = tend[l];
           if (!sim2d) t -= (fy_hi[l] - fy_lo[l]) * P.rdy;
           t -= (fz_hi[l] - fz_lo[l]) * P.rdz;

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) k_surrogate_fmav(const MlpWeights w, cons
     const long long p = base + q * 256;
 #pragma unroll
     for (int f = 0; f < 5; ++f)
-      if (p < npair) v[q][f] = __ldg(reinterpret_cast<const double2 *>(S.in[f]) + p);
+      if (p < npair) v[q][f] = reinterpret_cast<const double2 *>(S.in[f])[p];    // plain loads: outputs may alias inputs
   }
 #pragma unroll
   for (int q = 0; q < NV; ++q) {

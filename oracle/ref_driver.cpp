@@ -81,7 +81,7 @@ static void usage() {
     "ref_driver run nx= ny= nz= xlen= ylen= zlen= [nens=1] [init_data=supercell] [tracers=kessler|vapor]\n"
     "               [steps=10] [dt=0 (0 => dycore.compute_time_step)] [dycore=1] [micro=0] [sponge=0] [nudge=0]\n"
     "               [perturb=1] [in=state.bin] [out=state.bin] [out0=initial_state.bin] [bg=background.bin]\n"
-    "               [precl=precl.bin] [time=0|1 print seconds per step]\n"
+    "               [precl=precl.bin] [time=0|1 print seconds per step] [warmup=0 untimed steps first]\n"
     "               [enable_gravity=1] [hsponge=0 (simple_city: Horizontal_Sponge init(10,1) + apply(x1,x2) before the dycore)]\n"
     "               [sponge_ts=60] [imm=immersed_proportion.bin] [init_data=supercell|thermal|building|city]\n");
 }
@@ -92,7 +92,7 @@ static int mode_run(std::map<std::string,std::string> &kv) {
   auto gets = [&](const char *k, const char *d) { return kv.count(k) ? kv[k] : std::string(d); };
   int    nx = geti("nx",100), ny = geti("ny",1), nz = geti("nz",40), nens = geti("nens",1);
   double xlen = getd("xlen",100000), ylen = getd("ylen",100000), zlen = getd("zlen",20000);
-  int    steps = geti("steps",10);
+  int    steps = geti("steps",10), warmup = geti("warmup",0);     // warmup: untimed steps before the timed ones
   double dt_in = getd("dt",0.);
   bool   do_dycore = geti("dycore",1), do_micro = geti("micro",0), do_sponge = geti("sponge",0);
   bool   do_nudge = geti("nudge",0), do_perturb = geti("perturb",1), do_time = geti("time",0);
@@ -144,7 +144,8 @@ static int mode_run(std::map<std::string,std::string> &kv) {
 
   real dtphys = dt_in;
   auto t0 = std::chrono::steady_clock::now();
-  for (int s=0; s < steps; s++) {
+  for (int s=-warmup; s < steps; s++) {
+    if (s == 0) { yakl::fence(); t0 = std::chrono::steady_clock::now(); }
     if (dt_in <= 0.) dtphys = dycore.compute_time_step(coupler);
     if (do_hsponge) horiz_sponge.apply          ( coupler , dtphys , true , true , false , false );  // simple_city/driver.cpp:72
     if (do_dycore) dycore.time_step             ( coupler , dtphys );

@@ -105,3 +105,48 @@ def test_config3_block_full_physics_step():
         assert f[5 + t].min().item() >= 0.0
     assert precl.min().item() >= 0.0 and precl.max().item() > 0.0  # rain reached the ground somewhere
     dy.close()
+
+
+@pytest.mark.needs_reference
+def test_config2_two_steps_vs_compiled_reference(tmp_path):
+    """BASELINE config 2 at its full size against the reference itself: oracle/_ref/ref_driver_omp (the unmodified
+    reference, YAKL OpenMP backend) initialises the 512 x 512 x 128 supercell + thermal, dumps the state, takes two
+    dycore steps and dumps again; the GPU takes the same two steps from the same dump (DYC:81-198).  Tolerance: north_star's
+    1e-9 max relative difference per field.  Skipped where oracle/_ref was not built (it travels to the GPU box)."""
+    import json
+    import os
+    import subprocess
+    import _oracle as O
+    import torch
+    import miniweatherml_b200 as mw
+    if not os.path.exists(O.REF_DRIVER_OMP):
+        pytest.skip("oracle/_ref/ref_driver_omp not built")
+    nx = ny = int(os.environ.get("MW_FULLSIZE_N", "512"))
+    nz, steps = 128, 2
+    s0f, s1f, bgf = [str(tmp_path / n) for n in ("s0.bin", "s1.bin", "bg.bin")]
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1), GATOR_INITIAL_MB="4096")
+    out = subprocess.run([O.REF_DRIVER_OMP, "run", "nx=%d" % nx, "ny=%d" % ny, "nz=%d" % nz, "xlen=%g" % (nx * 1000.0),
+                          "ylen=%g" % (ny * 1000.0), "zlen=%g" % ZLEN, "tracers=vapor", "steps=%d" % steps,
+                          "out0=" + s0f, "out=" + s1f, "bg=" + bgf], env=env, capture_output=True, text=True, check=True,
+                         timeout=1500).stdout
+    meta = [json.loads(l) for l in out.splitlines() if l.startswith("{") and "C0" in l][-1]
+    shp = (6, nz, ny, nx)
+    s0 = np.fromfile(s0f).reshape(shp)
+    cfg = mw.make_config(nx, ny, nz, nx * 1000.0, ny * 1000.0, ZLEN, 1)
+    dy = mw.Dycore(cfg)
+    dy.set_background(np.fromfile(bgf))
+    f = [torch.tensor(s0[l], device="cuda") for l in range(6)]
+    del s0
+    for _ in range(steps):
+        dy.time_step(f, float(meta["dt"]))
+    torch.cuda.synchronize()
+    s1 = np.fromfile(s1f).reshape(shp)
+    for l in range(6):
+        a = f[l].cpu().numpy()
+        den = np.abs(s1[l]).max()
+        err = np.abs(a - s1[l]).max() / (den if den > 0 else 1.0)
+        assert err <= 1e-9, (l, err)
+    assert np.abs(s1[3]).max() > 1e-3                           # the thermal is rising: the comparison is not trivial
+    dy.close()
+    for p in (s0f, s1f, bgf):
+        os.remove(p)

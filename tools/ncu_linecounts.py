@@ -31,5 +31,5 @@ for ((f, ln), txt), r in zip(instrs, data):
     if not f.startswith(os.environ.get("MW_SRC", "dycore_kernels")) or not (lo <= ln <= hi): continue
     mo = re.match(r'\s*(@!?U?P[T\d]+\s+)?([A-Z0-9_.]+)', txt); op = mo.group(2) if mo else '?'
     a = agg[ln]; a[0] += int(r[iI]); a[1] += int(r[iSm]); a[2][op.split('.')[0]] += int(r[iI])
-for ln, a in sorted(agg.items(), key=lambda t: -t[1][0])[:25]:
+for ln, a in sorted(agg.items(), key=lambda t: t[0]):
     print(f"line {ln}: instr/cell {a[0]*32/cells:7.1f} samples {a[1]:6d} | " + ", ".join(f"{o} {32*c/cells:.0f}" for o, c in a[2].most_common(6)))
