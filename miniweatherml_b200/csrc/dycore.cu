@@ -2,8 +2,6 @@
 // scratch, the background profiles and the TMA descriptors, and sequences the kernels of one time_step
 // (reference: model/modules/dynamics_euler_stratified_wenofv.h:81-198).
 #include "dycore_kernels.cuh"
-#include "stage_ws.cuh"
-#include "stage_uj.cuh"
 #include "stage_cell.cuh"
 #include "comm.cuh"
 #include <cmath>
@@ -77,33 +75,12 @@ int encode_tensor_map_f64_4d(CUtensorMap *map, const void *base, const uint64_t 
 
 using namespace mw;
 
-// tile of columns one CTA owns (two threads per column) and CTAs resident per SM.  Variant 0: 32 x 8 (24 x 8 with >= 3
-// tracers so the CTA fits 227 KB of smem), one CTA per SM.  Variant 1: 16 x 8, two CTAs per SM, so that one CTA's
-// integer-heavy update phase overlaps the other's FP64-heavy reconstruction phase.
-template <int NT, int VAR> struct Tile {
-  static constexpr int X = VAR == 1 ? 16 : ((NT <= 1) ? 32 : 24), Y = 8, MINB = VAR == 1 ? 2 : 1;
-};
-// Variant 2: warp-specialised kernel (stage_ws.cuh), 16 x 8 tile, reconstruction and update warps run concurrently.
-// Read once per handle (mw_dycore_create), so that tests can switch variants inside one process.
-static int tile_variant(int nt) {
-  const char *e = getenv("MW_TILE_VARIANT");
-  int v = e ? atoi(e) : -1;                                // -1 = default choice (below)
-  const char *t = getenv("MW_NO_TMA");
-  if (t && atoi(t) != 0) v = 0;                            // the plain-load path exists in the phase kernel only
-  // default: the warp-specialised kernel; with <= 1 tracer its segment form (x/y reconstructions as sliding line segments)
-  // is 1.8 % faster, with 3 tracers 1 % slower (profiles/r01n_stage_seg_variant_ncu_summary.txt)
-  if (v == -1 || v == 5) return 5;                         // cell kernel (stage_cell.cuh), every tracer count
-  if (v == 4) return nt <= 3 ? 4 : 0;                    // ws kernel with segment reconstructions
-  if (v == 3) return nt <= 1 ? 3 : (nt <= 3 ? 2 : 0);    // uniform-jobs kernel (stage_uj.cuh) where it fits in smem
-  if (v == 2) return nt <= 3 ? 2 : 0;
-  return (nt <= 1) ? v : 0;
-}
-static int tile_x_of(int v, int nt) { return v == 5 ? 32 : (v >= 1 ? 16 : (nt <= 1 ? 32 : 24)); }
+// The stage kernel is the cell kernel of stage_cell.cuh: a 32 x 8 tile of columns per CTA, one thread per cell.
+constexpr int TILE_X = 32, TILE_Y = 8;
 
 struct mw_dycore {
   mw_config cfg;
   int N;
-  int variant = 5, tile_x = 32;        // stage kernel variant and its tile width, fixed at creation (tile height is 8)
   double dx, dy, dz;
   int pitch;
   long long zstride, vstride;
@@ -119,7 +96,6 @@ struct mw_dycore {
   mw_comm *comm = nullptr;
   long long launches = 0;
   int use_tma = 1;
-  unsigned long long *prof = nullptr;  // MW_STAGE_PROF=1: wait accounting of k_stage_uj (managed memory), printed on destroy
   // staging for the *_host entry point
   double *dev_fields[NUM_STATE + MW_MAX_TRACERS] = {nullptr};
   bool dev_fields_alloc = false;
@@ -168,7 +144,6 @@ static StageParams base_params(const mw_dycore *h) {
   P.positive_mask = pm;
   P.use_tma = h->use_tma;
   P.tile_mode = 0;
-  P.prof = h->prof;
   // FCT donors across interior rank boundaries (never across the global periodic seam, see StageParams)
   P.mult_W = (h->dir_active[0] && c.px > 0) ? h->mrecv[0] : nullptr;
   P.mult_E = (h->dir_active[1] && c.px < c.nproc_x - 1) ? h->mrecv[1] : nullptr;
@@ -218,10 +193,6 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   h->qbytes = (size_t) h->N * h->vstride * sizeof(double);
   const char *e = getenv("MW_NO_TMA");
   h->use_tma = (e && atoi(e) != 0) ? 0 : 1;
-  h->variant = tile_variant(cfg->num_tracers);
-  h->tile_x = tile_x_of(h->variant, cfg->num_tracers);
-  const char *pe = getenv("MW_STAGE_PROF");
-  if (pe && atoi(pe) != 0 && cudaMallocManaged(&h->prof, 8 * sizeof(unsigned long long)) == cudaSuccess) memset(h->prof, 0, 64);
   const int T = cfg->num_tracers > 0 ? cfg->num_tracers : 1;
   const size_t nzl = cfg->nz, nyl = cfg->ny, nxl = cfg->nx;
   cudaError_t ce = cudaSuccess;
@@ -242,10 +213,10 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   for (int b = 0; b < 3; ++b) {
     const uint64_t dims[4] = {(uint64_t) h->pitch, (uint64_t) (cfg->ny + 2 * HALO), (uint64_t) cfg->nz, (uint64_t) h->N};
     const uint64_t str[3] = {(uint64_t) h->pitch * 8, (uint64_t) h->zstride * 8, (uint64_t) h->vstride * 8};
-    const uint32_t box[4] = {(uint32_t) h->tile_x + 2 * HALO, 8 + 2 * HALO, 1, (uint32_t) h->N};
+    const uint32_t box[4] = {TILE_X + 2 * HALO, TILE_Y + 2 * HALO, 1, (uint32_t) h->N};
     rc = encode_tensor_map_f64_4d(&h->tmap[b], h->q[b], dims, str, box);
     if (rc != MW_OK) { mw_dycore_destroy(h); return rc; }
-    const uint32_t boxi[4] = {34, 8, 1, (uint32_t) h->N};   // CellCfg::IW x TY
+    const uint32_t boxi[4] = {TILE_X + 2, TILE_Y, 1, (uint32_t) h->N};   // CellCfg::IW x TY
     rc = encode_tensor_map_f64_4d(&h->tmapI[b], h->q[b], dims, str, boxi);
     if (rc != MW_OK) { mw_dycore_destroy(h); return rc; }
   }
@@ -255,15 +226,6 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
 
 extern "C" int mw_dycore_destroy(mw_dycore *h) {
   if (!h) return MW_OK;
-  if (h->prof) {
-    cudaDeviceSynchronize();
-    const unsigned long long *p = h->prof;
-    const double n = p[6] ? (double) p[6] : 1.0;
-    fprintf(stderr, "[mw stage prof] CTAs %llu  R: total %.0f cyc, wait-for-U %.1f%%, wait-for-TMA %.1f%%   U: total %.0f cyc, wait-for-R %.1f%%, "
-            "named barriers %.1f%%\n", p[6], p[0] / n, 100.0 * p[1] / (p[0] + 1.0), 100.0 * p[2] / (p[0] + 1.0), p[3] / n,
-            100.0 * p[4] / (p[3] + 1.0), 100.0 * p[5] / (p[3] + 1.0));
-    cudaFree(h->prof);
-  }
   for (int b = 0; b < 3; ++b) cudaFree(h->q[b]);
   cudaFree(h->flux_x); cudaFree(h->flux_y); cudaFree(h->flux_z); cudaFree(h->mult); cudaFree(h->bg);
   if (h->dev_fields_alloc) for (int f = 0; f < h->N; ++f) cudaFree(h->dev_fields[f]);
@@ -419,32 +381,8 @@ static int exchange_mult(mw_dycore *h, cudaStream_t st) {
   return exchange(h, h->msend, h->mrecv, h->mcount, st);
 }
 
-static int finish_stage(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st);
-static int finish_stage_local(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st, bool mult_done);
-template <int NT, int VAR>
-static int launch_stage_v(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st) {
-  constexpr int TILE_X = Tile<NT, VAR>::X, TILE_Y = Tile<NT, VAR>::Y, MINB = Tile<NT, VAR>::MINB;
-  using C = StageCfg<NT, TILE_X, TILE_Y>;
-  const size_t smem = C::smem_bytes(P.nz);
-  MW_REQUIRE(smem <= 227 * 1024, "stage kernel needs %zu bytes of shared memory (nz = %d, %d tracers): over the 227 KB limit",
-             smem, P.nz, NT);
-  static size_t attr_set = 0;
-  if (attr_set < smem) {
-    MW_CUDA_OK(cudaFuncSetAttribute(k_stage<NT, TILE_X, TILE_Y, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    attr_set = smem;
-  }
-  dim3 grid((P.nx + TILE_X - 1) / TILE_X, (P.ny + TILE_Y - 1) / TILE_Y);
-  if (h->timing) {
-    while (h->ev.size() < (size_t) (4 + 2 * h->n_stage_timed)) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
-    cudaEventRecord(h->ev[2 + 2 * h->n_stage_timed], st);
-  }
-  k_stage<NT, TILE_X, TILE_Y, MINB><<<grid, C::NTHR, smem, st>>>(h->tmap[in_buf], P);
-  MW_CUDA_OK(cudaGetLastError());
-  if (h->timing) { cudaEventRecord(h->ev[3 + 2 * h->n_stage_timed], st); h->n_stage_timed++; }
-  h->launches++;
-  return finish_stage(h, P, NT, st);
-}
 // tracer finish (FCT-scaled divergence, RK, clip); with decomposed directions the neighbours' FCT factors come first
+static int exchange_halos(mw_dycore *h, double *q, cudaStream_t st);
 static int finish_stage_local(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st, bool mult_done = false) {
   if (nt > 0) {
     if (!mult_done) {
@@ -480,35 +418,23 @@ static int exchange_halos_async(mw_dycore *h, double *q, cudaStream_t st) {
   h->halo_inflight = true;
   return MW_OK;
 }
-// KIND 2: warp-specialised kernel with register z windows (stage_ws.cuh); KIND 3: uniform-jobs kernel (stage_uj.cuh)
-template <int NT, int KIND> struct WsKernel;
-template <int NT> struct WsKernel<NT, 5> {                       // cell kernel (stage_cell.cuh): 32 x 8 tile, one thread per cell
+// The cell kernel (stage_cell.cuh) with TMA box loads, or -- MW_NO_TMA=1, tests -- the same kernel filling its planes with plain loads
+template <int NT> struct StageKernel {
   using C = CellCfg<NT>;
-  static constexpr int TX = 32;
-  static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P) { k_stage_cell<NT><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P); }
-  static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_cell<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
+  static constexpr int TX = TILE_X;
+  static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P) {
+    if (h->use_tma) k_stage_cell<NT, true><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P);
+    else k_stage_cell<NT, false><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P);
+  }
+  static cudaError_t attr() {
+    cudaError_t e = cudaFuncSetAttribute(k_stage_cell<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_stage_cell<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+  }
 };
-template <int NT> struct WsKernel<NT, 2> {
-  using C = WsCfg<NT, 16, 8>;
-  static constexpr int TX = 16;
-  static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P) { k_stage_ws<NT, 16, 8><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], P); }
-  static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_ws<NT, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
-};
-template <int NT> struct WsKernel<NT, 4> {                       // ws kernel with segment reconstructions (SEG = true)
-  using C = WsCfg<NT, 16, 8>;
-  static constexpr int TX = 16;
-  static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P) { k_stage_ws<NT, 16, 8, true><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], P); }
-  static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_ws<NT, 16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
-};
-template <int NT> struct WsKernel<NT, 3> {
-  using C = UjCfg<NT, 16, 8>;
-  static constexpr int TX = 16;
-  static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P) { k_stage_uj<NT, 16, 8><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], P); }
-  static cudaError_t attr() { return cudaFuncSetAttribute(k_stage_uj<NT, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM); }
-};
-template <int NT, int KIND = 2>
-static int launch_stage_ws(mw_dycore *h, const StageParams &P0, int in_buf, cudaStream_t st, bool last) {
-  using K = WsKernel<NT, KIND>;
+template <int NT>
+static int launch_stage(mw_dycore *h, const StageParams &P0, int in_buf, cudaStream_t st, bool last) {
+  using K = StageKernel<NT>;
   static bool attr_set = false;
   if (!attr_set) {
     MW_CUDA_OK(K::attr());
@@ -556,16 +482,6 @@ static int launch_stage_ws(mw_dycore *h, const StageParams &P0, int in_buf, cuda
   if (rc != MW_OK) return rc;
   return last ? MW_OK : exchange_halos_async(h, P0.qout, st);      // the last stage's halos are never read
 }
-template <int NT>
-static int launch_stage(mw_dycore *h, const StageParams &P, int in_buf, cudaStream_t st, bool last) {
-  if (h->variant == 5) return launch_stage_ws<NT, 5>(h, P, in_buf, st, last);
-  if constexpr (NT <= 1) { if (h->variant == 3) return launch_stage_ws<NT, 3>(h, P, in_buf, st, last); }
-  if constexpr (NT <= 3) { if (h->variant == 4) return launch_stage_ws<NT, 4>(h, P, in_buf, st, last); }
-  if constexpr (NT <= 3) { if (h->variant == 2) return launch_stage_ws<NT, 2>(h, P, in_buf, st, last); }
-  if constexpr (NT <= 1) { if (h->variant == 1) return launch_stage_v<NT, 1>(h, P, in_buf, st); }
-  return launch_stage_v<NT, 0>(h, P, in_buf, st);
-}
-
 template <int NT>
 static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaStream_t st) {
   const mw_config &c = h->cfg;
@@ -716,9 +632,9 @@ extern "C" int mw_host_pipeline_plan(int ny, int rows_per_slab, int num_tracers,
   return MW_OK;
 }
 
-template <int NT, int KIND>
+template <int NT>
 static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double dt_phys, int rows_per_slab, int ncycles) {
-  using K = WsKernel<NT, KIND>;
+  using K = StageKernel<NT>;
   const mw_config &c = h->cfg;
   static bool attr_set = false;
   if (!attr_set) { MW_CUDA_OK(K::attr()); attr_set = true; }
@@ -882,34 +798,27 @@ extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields
   // rows with about one wave of tiles (148 SMs, one CTA each) per slab launch.  MW_HOST_SLAB_ROWS overrides (0 = off).
   int rows_per_slab = 0;
   {
-    const int nbx = (c.nx + h->tile_x - 1) / h->tile_x;
+    const int nbx = (c.nx + TILE_X - 1) / TILE_X;
     int tile_rows = std::max(1, 148 / nbx);
     rows_per_slab = 8 * tile_rows;
     const char *e = getenv("MW_HOST_SLAB_ROWS");
     if (e) rows_per_slab = (atoi(e) / 8) * 8;
   }
-  const int variant = h->variant;
   const int ncycles = (int) ceil(dt_phys / mw_dycore_compute_time_step(h));                 // DYC:104-108
   // decomposed runs: every rank must walk the same schedule, so the blocks must be equal
   const bool equal_blocks = c.nproc_x * c.nproc_y == 1 ||
                             (h->comm && c.nx_glob % c.nproc_x == 0 && c.ny_glob % c.nproc_y == 0 && c.nx == c.nx_glob / c.nproc_x && c.ny == c.ny_glob / c.nproc_y);
-  const bool pipelined = rows_per_slab >= 8 && equal_blocks && c.ny_glob > 1 && (variant == 2 || variant == 4 || variant == 5) &&
-                         c.ny / rows_per_slab >= 4;
+  const bool pipelined = rows_per_slab >= 8 && equal_blocks && c.ny_glob > 1 && c.ny / rows_per_slab >= 4;
   if (pipelined) {
     MW_CUDA_OK(cudaDeviceSynchronize());                  // the non-blocking streams do not order against earlier default-stream work
     int rc = 1;
-#define MW_HOST_PIPE(NT)                                                                                          \
-  rc = variant == 5 ? host_step_pipelined<NT, 5>(h, host_fields, dt_phys, rows_per_slab, ncycles)                 \
-     : variant == 4 ? host_step_pipelined<NT, 4>(h, host_fields, dt_phys, rows_per_slab, ncycles)                 \
-                    : host_step_pipelined<NT, 2>(h, host_fields, dt_phys, rows_per_slab, ncycles)
     switch (c.num_tracers) {
-      case 0: MW_HOST_PIPE(0); break;
-      case 1: MW_HOST_PIPE(1); break;
-      case 2: MW_HOST_PIPE(2); break;
-      case 3: MW_HOST_PIPE(3); break;
-      case 4: if (variant == 5) rc = host_step_pipelined<4, 5>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
+      case 0: rc = host_step_pipelined<0>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
+      case 1: rc = host_step_pipelined<1>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
+      case 2: rc = host_step_pipelined<2>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
+      case 3: rc = host_step_pipelined<3>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
+      case 4: rc = host_step_pipelined<4>(h, host_fields, dt_phys, rows_per_slab, ncycles); break;
     }
-#undef MW_HOST_PIPE
     if (rc != 1) return rc;                               // 1 = grid too small for the chain: unpipelined path below
   }
   for (int f = 0; f < h->N; ++f) MW_CUDA_OK(cudaMemcpyAsync(h->dev_fields[f], host_fields[f], bytes, cudaMemcpyHostToDevice, 0));
@@ -937,7 +846,7 @@ extern "C" int mw_dycore_attach_comm(mw_dycore *h, mw_comm *comm) {
   h->dir_active[2] = h->dir_active[3] = (c.nproc_y > 1) && !sim2d;
   {
     const char *e = getenv("MW_NO_OVERLAP");
-    h->overlap = (h->dir_active[0] || h->dir_active[2]) && h->variant >= 2 && !(e && atoi(e) != 0);
+    h->overlap = (h->dir_active[0] || h->dir_active[2]) && !(e && atoi(e) != 0);
     if (h->overlap && !h->cs) {
       // high priority: the few boundary CTAs and the pack / NCCL / unpack kernels are dispatched ahead of the queued
       // interior CTAs as SMs free up, so they never form a tail of their own

@@ -70,8 +70,7 @@ struct WenoConsts { double c133, c524, k2, k2e, k3, k4, i12, i24, tenth, e20; };
 __constant__ WenoConsts wc = {13.0 / 3.0, 5.0 / 24.0, 13.0 / 192.0, 7.0 / 160.0, 3129.0 / 2880.0, 87617.0 / 20160.0,
                               1.0 / 12.0, 1.0 / 24.0, 0.1, 1.e-20};
 // The part of the reconstruction after the differences: centre value s2, the two inner first differences, the three
-// second differences and Q = (13/3 * D) * D of each.  weno5_edges (one stencil) and weno5_segment (a run of consecutive
-// cells along a line, which shares the differences between neighbouring stencils) both end here, so they give the same bits.
+// second differences and Q = (13/3 * D) * D of each.
 __device__ __forceinline__ void weno5_core(double s2, double d12, double d23, double DL, double DC, double DR,
                                            double QL, double QC, double QR, double &v_lo, double &v_hi) {
   const double b1L = fma(2.0, d12, DL), b1C = d12 + d23, b1R = fma(2.0, d23, -DR);
@@ -102,9 +101,11 @@ __device__ __forceinline__ void weno5_core(double s2, double d12, double d23, do
   od = fma(nR, b1R, od);
   od = fma(nH, h, od);
   ev = fma(inv * wc.i12, ev, s2);
-  od = (inv * 0.25) * od;
-  v_lo = ev - od;
-  v_hi = ev + od;
+  // explicit fma: a caller that uses only one of the two edge values (the ring reconstructions of the cell kernel)
+  // must get the same bits as one that uses both, or the two tiles sharing a face would disagree on its flux
+  const double c = inv * 0.25;
+  v_lo = fma(-c, od, ev);
+  v_hi = fma(c, od, ev);
 }
 __device__ __forceinline__ void weno5_edges(double s0, double s1, double s2, double s3, double s4,
                                             double &v_lo, double &v_hi) {
@@ -112,19 +113,6 @@ __device__ __forceinline__ void weno5_edges(double s0, double s1, double s2, dou
   const double DL = d12 - d01, DC = d23 - d12, DR = d34 - d23;               // second differences
   weno5_core(s2, d12, d23, DL, DC, DR, (wc.c133 * DL) * DL, (wc.c133 * DC) * DC, (wc.c133 * DR) * DR, v_lo, v_hi);
 }
-// NJ consecutive cells of a line from their NJ + 4 values: cell c uses s[c .. c+4].  First and second differences and the
-// 13/3 D^2 terms are formed once per value instead of once per stencil (9 fewer fp64 operations per cell).
-template <int NJ>
-__device__ __forceinline__ void weno5_segment(const double (&s)[NJ + 4], double (&lo)[NJ], double (&hi)[NJ]) {
-  double d[NJ + 3], D[NJ + 2], Q[NJ + 2];
-#pragma unroll
-  for (int j = 0; j < NJ + 3; ++j) d[j] = s[j + 1] - s[j];
-#pragma unroll
-  for (int j = 0; j < NJ + 2; ++j) { D[j] = d[j + 1] - d[j]; Q[j] = (wc.c133 * D[j]) * D[j]; }
-#pragma unroll
-  for (int c = 0; c < NJ; ++c) weno5_core(s[c + 2], d[c + 1], d[c + 2], D[c], D[c + 1], D[c + 2], Q[c], Q[c + 1], Q[c + 2], lo[c], hi[c]);
-}
-
 // ----------------------------------------------------------------------------------------------------------
 // mbarrier + TMA (cp.async.bulk.tensor) wrappers -- raw PTX, no CUTLASS
 // ----------------------------------------------------------------------------------------------------------
@@ -136,21 +124,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Blocking wait on an mbarrier phase.  try_wait suspends the thread in hardware until the phase completes or the time hint
 // (ns) expires, so a waiting warp costs a handful of issue slots per hint period instead of polling -- issue slots are what
@@ -169,10 +142,6 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {
     if (spin > (1 << 22)) __trap();
   }
 }
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
 // generic-proxy writes/reads of a smem buffer must be ordered before the async proxy (TMA) overwrites it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

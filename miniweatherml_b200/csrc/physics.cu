@@ -30,12 +30,69 @@ struct KesslerParams {
   double *bnd;                   // [ceil(nz/KES_LPT)-1][ncol]: initial rho_r of the first level of chunks 1, 2, ...
 };
 
+// exp and log for the microphysics, with every coefficient in constant memory (an operand of the DFMA itself).  The
+// library versions spend as many instructions building their 64-bit constants in registers as on arithmetic, and on
+// B200 each of those costs an issue slot next to the FP64 pipe (tools/issue_probe.cu).  Accuracy: a few 1e-16
+// relative, far inside the 1e-9 tolerance of the path; arguments outside the fast range go to the library.
+struct KesMath {
+  double e[14];            // 1/k!, k = 0..13
+  double l[10];            // 2/(2n+1), n = 1..10
+  double l2e, ln2hi, ln2lo, rnd;
+};
+__constant__ KesMath km = {
+    {1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664, 0.0083333333333333332, 0.0013888888888888889,
+     0.00019841269841269841, 2.4801587301587302e-05, 2.7557319223985893e-06, 2.7557319223985888e-07,
+     2.505210838544172e-08, 2.08767569878681e-09, 1.6059043836821613e-10},
+    {0.66666666666666663, 0.40000000000000002, 0.2857142857142857, 0.22222222222222221, 0.18181818181818182,
+     0.15384615384615385, 0.13333333333333333, 0.11764705882352941, 0.10526315789473684, 0.095238095238095233},
+    1.4426950408889634, 0.69314718036912382, 1.9082149292705877e-10, 6755399441055744.0};
+
+__device__ __noinline__ double kes_exp_lib(double x) { return exp(x); }
+__device__ __noinline__ double kes_log_lib(double x) { return log(x); }
+
+// exp(x): x = k ln2 + r, |r| <= ln2/2, Taylor polynomial of degree 13 (remainder < 2e-16), scaled by 2^k through the
+// exponent field.  exp(-inf) = 0 and everything below -708 flushes to 0 (the results only scale mixing ratios).
+__device__ __forceinline__ double kes_exp(double x) {
+  if (x < -708.0) return 0.0;
+  if (!(x <= 708.0)) return kes_exp_lib(x);                                   // NaN, +inf, overflow range: library
+  const double t = fma(x, km.l2e, km.rnd);                           // round(x / ln2) in the low word
+  const int k = __double2loint(t);
+  const double kd = t - km.rnd;
+  double r = fma(kd, -km.ln2hi, x);
+  r = fma(kd, -km.ln2lo, r);
+  double p = km.e[13];
+#pragma unroll
+  for (int i = 12; i >= 0; --i) p = fma(p, r, km.e[i]);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));   // p in [0.7, 1.42), |k| <= 1022
+}
+
+// log(x), x > 0 normal: x = m 2^e with m in [sqrt(1/2), sqrt(2)), log m = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716,
+// odd series to s^21 (remainder < 3e-17).  log(0) = -inf inline (a dry cell is the common case); negative, subnormal,
+// infinite and NaN arguments go to the library.
+__device__ __forceinline__ double kes_log(double x) {
+  if (x == 0.0) return __longlong_as_double(0xfff0000000000000ll);
+  int hi = __double2hiint(x);
+  if (hi < 0x00100000 || hi >= 0x7ff00000) return kes_log_lib(x);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  if (hi >= 0x3ff6a09f) { hi -= 0x00100000; e += 1; }               // m >= ~sqrt(2): halve
+  const double m = __hiloint2double(hi, __double2loint(x));
+  const double s = (m - 1.0) * fast_rcp(m + 1.0);
+  const double z = s * s;
+  double p = km.l[9];
+#pragma unroll
+  for (int i = 8; i >= 0; --i) p = fma(p, z, km.l[i]);
+  const double lm = fma(s * z, p, s + s);
+  const double ed = (double) e;
+  return fma(ed, km.ln2hi, fma(ed, km.ln2lo, lm));
+}
+
 // x^y for x >= 0 from a logarithm that is shared between the powers of one argument: exp(y * log x).  log(0) = -inf
 // gives exp(-inf) = 0 = pow(0, y) for the positive exponents used here; a negative x gives NaN like pow().  Relative
 // error <= (|y log x| + 1) ulp, i.e. a few 1e-15 for the arguments of this scheme (tolerance of the path: 1e-9).
-__device__ __forceinline__ double pow_from_log(double logx, double y) { return exp(y * logx); }
+__device__ __forceinline__ double pow_from_log(double logx, double y) { return kes_exp(y * logx); }
 
-// terminal fall speed, KW eq. 2.15 (KES:260,331): 36.34 * (qr*r)^0.1364 * rhalf, from log(qr*r)
+// terminal fall speed, KW eq. 2.15 (KES:260,331): 36.34 * (qr*r)^0.1364 * rhalf, from kes_log(qr*r)
 __device__ __forceinline__ double kessler_velqr(double log_rq, double rhalf) {
   return 36.34 * pow_from_log(log_rq, 0.1364) * rhalf;
 }
@@ -54,7 +111,7 @@ __global__ void __launch_bounds__(256) k_kessler_dtmin(const KesslerParams K) {
     if (c < n) {                                                      // the top level does not enter (KES:262)
       const double rho = K.rho_dry[c], rho0 = K.rho_dry[i];
       const double qr = rr / rho;
-      const double vel = kessler_velqr(log(qr * (0.001 * rho)), sqrt(rho0 / rho));
+      const double vel = kessler_velqr(kes_log(qr * (0.001 * rho)), sqrt(rho0 / rho));
       const double d = (vel > 1.e-10) ? 0.8 * K.dz / vel : K.dt;      // z(k+1)-z(k) = dz
       m = fmin(m, d);
     }
@@ -73,7 +130,7 @@ __global__ void k_kessler_split(const KesslerParams K) {
 __device__ __forceinline__ double qdiv(double a, double b) { return a * fast_rcp(b); }
 
 // One cell through one sedimentation sub-cycle's adjustment (KES:304-328).  State (theta, qv, qc, qr) in and out;
-// r = 0.001 rho, pk the Exner function, pc = 3.8 / (pk^(cp/Rd) psl), lq = log(qr) of the incoming qr.
+// r = 0.001 rho, pk the Exner function, pc = 3.8 / (pk^(cp/Rd) psl), lq = kes_log(qr) of the incoming qr.
 __device__ __forceinline__ void kessler_adjust(double &theta, double &qv, double &qc, double &qr, double lq, double sed,
                                                double r, double pk, double pc, double dt0, double lv, double cp) {
   const double qrprod = qc - qdiv(qc - dt0 * fmax(0.001 * (qc - 0.001), 0.), 1 + dt0 * 2.2 * pow_from_log(lq, 0.875));
@@ -81,10 +138,10 @@ __device__ __forceinline__ void kessler_adjust(double &theta, double &qv, double
   qr = fmax(qr + qrprod + sed, 0.);
   const double tmp = pk * theta - 36.;
   const double itmp = fast_rcp(tmp);
-  const double qvs = pc * exp(17.27 * (pk * theta - 273.) * itmp);
+  const double qvs = pc * kes_exp(17.27 * (pk * theta - 273.) * itmp);
   const double iqvs = fast_rcp(qvs);
   const double prod = qdiv(qv - qvs, 1. + qvs * (4093. * lv / cp) * (itmp * itmp));
-  const double lrq = log(r * qr);
+  const double lrq = kes_log(r * qr);
   const double tmp1 = dt0 * qdiv((1.6 + 124.9 * pow_from_log(lrq, 0.2046)) * pow_from_log(lrq, 0.525),
                                  2550000. * pc * (iqvs * (1. / 3.8)) + 540000.) *
                       (fmax(qvs - qv, 0.) * (fast_rcp(r) * iqvs));
@@ -115,7 +172,7 @@ __global__ void __launch_bounds__(256) k_kessler_single(const KesslerParams K) {
   const double rho_sfc = K.rho_dry[i];
   long long c = (long long) k0 * nc + i;
   double rho1 = K.rho_dry[c], irho1 = fast_rcp(rho1), qr1 = K.rho_r[c] * irho1, r1 = 0.001 * rho1;
-  double vel1 = kessler_velqr(log(qr1 * r1), sqrt(rho_sfc * irho1));
+  double vel1 = kessler_velqr(kes_log(qr1 * r1), sqrt(rho_sfc * irho1));
   if (k0 == 0) K.precl[i] = rho_sfc * qr1 * vel1 / rhoqr;            // KES:291, 332-334 with rainsplit = 1
   const double idz = 1.0 / K.dz, ip0 = 1.0 / K.p0;
   const int k1 = min(k0 + KES_LPT, nz);
@@ -137,17 +194,17 @@ __global__ void __launch_bounds__(256) k_kessler_single(const KesslerParams K) {
       irho1 = fast_rcp(rho1);
       qr1 = rr_n * irho1;
       r1 = 0.001 * rho1;
-      vel1 = kessler_velqr(log(qr1 * r1), sqrt(rho_sfc * irho1));
+      vel1 = kessler_velqr(kes_log(qr1 * r1), sqrt(rho_sfc * irho1));
       sed = dt0 * (r1 * qr1 * vel1 - r * qr * vel) * (1000.0 * irho * idz);     // KES:296-297: / (r dz), r = 0.001 rho
     } else {
       sed = -dt0 * qr * vel * (2.0 * idz);                           // KES:294
     }
     double qv = rv * irho, qc = rc * irho;                           // KES:136-144
     const double pratio = (K.R_d * rho * tk + K.R_v * rv * tk) * ip0;
-    const double pk = pow_from_log(log(pratio), kappa);
+    const double pk = pow_from_log(kes_log(pratio), kappa);
     double theta = qdiv(tk, pk);
     const double pc = qdiv(3.8, pratio * psl);                       // KES:258: pk^(cp/Rd) is the pressure ratio itself
-    kessler_adjust(theta, qv, qc, qr, log(qr), sed, r, pk, pc, dt0, lv, cp);
+    kessler_adjust(theta, qv, qc, qr, kes_log(qr), sed, r, pk, pc, dt0, lv, cp);
     K.rho_v[c] = qv * rho; K.rho_c[c] = qc * rho; K.rho_r[c] = qr * rho; K.temp[c] = theta * pk;   // KES:154-161
     c += nc;
     tk = tk_n; rv = rv_n; rc = rc_n;
@@ -179,16 +236,16 @@ __global__ void __launch_bounds__(128) k_kessler_split_columns(const KesslerPara
     const double tk = K.temp[c], rv = K.rho_v[c];
     double qr = K.rho_r[c] / rho, qv = rv / rho, qc = K.rho_c[c] / rho;
     const double pratio = (K.R_d * rho * tk + K.R_v * rv * tk) / K.p0;
-    const double pk = pow_from_log(log(pratio), kappa);
+    const double pk = pow_from_log(kes_log(pratio), kappa);
     double theta = tk / pk;
     const double pc = 3.8 / (pratio * psl);
     for (int nt = 0; nt < rainsplit; ++nt) {
-      const double vel = kessler_velqr(log(qr * r), rhalf);
+      const double vel = kessler_velqr(kes_log(qr * r), rhalf);
       if (k == 0) precl += rho_sfc * qr * vel / rhoqr;               // KES:291
       const double sed = (k < nz - 1) ? dt0 * (r_up * hq[nt] * hv[nt] - r * qr * vel) / (r * K.dz)
                                       : -dt0 * qr * vel / (0.5 * K.dz);
       hq[nt] = qr; hv[nt] = vel;                                     // what the level below reads in its sub-cycle nt
-      kessler_adjust(theta, qv, qc, qr, log(qr), sed, r, pk, pc, dt0, lv, cp);
+      kessler_adjust(theta, qv, qc, qr, kes_log(qr), sed, r, pk, pc, dt0, lv, cp);
     }
     K.rho_v[c] = qv * rho; K.rho_c[c] = qc * rho; K.rho_r[c] = qr * rho; K.temp[c] = theta * pk;
     r_up = r;

@@ -5,7 +5,7 @@
 // else issues next to it (tools/issue_probe.cu), so a stage costs 2*F + O issue cycles (F fp64, O other instructions).
 // F is fixed by the algorithm (18 WENO5 reconstructions per cell and stage); the round-1 kernels spent O = 2100 on
 // descriptor decoding, shared-memory hand-offs between reconstruction and flux warps, register-window shifts, loop
-// control and barrier polling.  Here one thread owns one cell of a 32 x 8 tile and ALL variables of it, so that
+// control and barrier polling.  Here one thread owns one cell of a TX x 8 tile and ALL variables of it, so that
 //   * every stencil load is one LDS with a compile-time offset from a per-thread base (x, y: the haloed plane of the
 //     level; z: a five-level window of interior planes in shared memory -- no register window, no shifts),
 //   * edge values, pressures and fluxes stay in registers: x neighbours trade them by warp shuffles (a warp is one
@@ -34,8 +34,10 @@ struct CellCfg {
   static constexpr int OFF_H = 0;
   static constexpr int OFF_I = OFF_H + NHS * HSLOTP;
   static constexpr int OFF_HY = OFF_I + NIS * ISLOT;           // [NV1][TY+1][TX] high-y edge values; row r = cell y = r-1
-  static constexpr int OFF_FY = OFF_HY + NV1 * (TY + 1) * TX;  // [N][TY+1][TX]   y face fluxes; row r = low face of cell y = r
-  static constexpr int OFF_RYL = OFF_FY + N * (TY + 1) * TX;   // [NV1][TX]       low-y edge values of the ring row y = TY
+  // y face fluxes [N][TY+1][TX], row r = low face of cell y = r: they take the place of the high-y edge values -- the flux
+  // of face (r, x) is written by the one thread that read HY(., r, x) as the low side of that face, after it read it
+  static constexpr int OFF_FY = OFF_HY;
+  static constexpr int OFF_RYL = OFF_HY + NV1 * (TY + 1) * TX; // [NV1][TX]       low-y edge values of the ring row y = TY
   static constexpr int OFF_RXH = OFF_RYL + NV1 * TX;           // [NV1][TY]       high-x edge values of the ring column x = -1
   static constexpr int OFF_RXL = OFF_RXH + NV1 * TY;           // [NV1][TY]       low-x edge values of the ring column x = TX
   static constexpr int OFF_BAR = OFF_RXL + NV1 * TY;           // NHS + NIS mbarriers
@@ -73,10 +75,11 @@ __device__ __forceinline__ void face_flux(const double (&L)[N], const double (&R
   }
 }
 
-__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
-__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+// neighbour exchange along x inside a tile row (W = TX lanes)
+template <int W> __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1, W); }
+template <int W> __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1, W); }
 
-template <int NT>
+template <int NT, bool TMA>
 __global__ void __launch_bounds__(CellCfg<NT>::NTHR, 1)
 k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ CUtensorMap tmapI, const StageParams P) {
   using C = CellCfg<NT>;
@@ -104,13 +107,37 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     mbar_expect_tx(&ibar[lev % NIS], (uint32_t) (C::ISLOT * 8));
     tma_load_4d(sm + C::OFF_I + (lev % NIS) * C::ISLOT, &tmapI, &ibar[lev % NIS], i0 + HALO - C::IXO, j0 + HALO, lev, 0);
   };
-  if (tid == 0) {
-    for (int s = 0; s < NHS + NIS; ++s) mbar_init(&hbar[s], 1);
-    mbar_fence_init();
-    tma_prefetch_desc(&tmapH);
-    tma_prefetch_desc(&tmapI);
-    for (int lev = 0; lev < 4 && lev < nz; ++lev) load_i(lev);
-    for (int lev = 0; lev < NHS && lev < nz; ++lev) load_h(lev);
+  // MW_NO_TMA=1 (tests): the same boxes filled with plain loads by all threads, zero outside the arrays like TMA; the
+  // CTA barriers of the level loop order them, so the mbarrier waits are skipped
+  constexpr bool use_tma = TMA;
+  auto plain_h = [&](int lev) {
+    double *dst = sm + C::OFF_H + (lev % NHS) * C::HSLOTP;
+    for (int idx = tid; idx < C::HSLOT; idx += C::NTHR) {
+      const int l = idx / PLANE, c = idx % PLANE, jh = j0 + c / PX, ih = i0 + c % PX;
+      dst[idx] = (jh < P.ny + 2 * HALO && ih < P.pitch)
+                     ? P.qin[(long long) l * P.vstride + (long long) lev * P.zstride + (long long) jh * P.pitch + ih] : 0.0;
+    }
+  };
+  auto plain_i = [&](int lev) {
+    double *dst = sm + C::OFF_I + (lev % NIS) * C::ISLOT;
+    for (int idx = tid; idx < C::ISLOT; idx += C::NTHR) {
+      const int l = idx / IPL, c = idx % IPL, jh = j0 + HALO + c / C::IW, ih = i0 + HALO - C::IXO + c % C::IW;
+      dst[idx] = (jh < P.ny + 2 * HALO && ih < P.pitch)
+                     ? P.qin[(long long) l * P.vstride + (long long) lev * P.zstride + (long long) jh * P.pitch + ih] : 0.0;
+    }
+  };
+  if (use_tma) {
+    if (tid == 0) {
+      for (int s = 0; s < NHS + NIS; ++s) mbar_init(&hbar[s], 1);
+      mbar_fence_init();
+      tma_prefetch_desc(&tmapH);
+      tma_prefetch_desc(&tmapI);
+      for (int lev = 0; lev < 4 && lev < nz; ++lev) load_i(lev);
+      for (int lev = 0; lev < NHS && lev < nz; ++lev) load_h(lev);
+    }
+  } else {
+    for (int lev = 0; lev < 4 && lev < nz; ++lev) plain_i(lev);
+    for (int lev = 0; lev < NHS && lev < nz; ++lev) plain_h(lev);
   }
 
   // ---- my ring jobs (fixed for the whole kernel): job j = round * NTHR + tid; the (rho theta)' jobs come first so
@@ -157,7 +184,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
   };
   double hiz_prev[N], p_hiz_prev, fz_lo[N];
   // z reconstruction of level kc -> lo / hi edge values and pressures (edge profiles kc and kc + 1)
-  auto zrecon = [&](int kc, double (&lo)[N], double (&hi)[N], double &p_lo, double &p_hi) {
+  auto zrecon = [&](int kc, double (&lo)[N], double (&hi)[N], double &p_lo, double &p_hi, int &big) {
     const double *w0 = zslot(kc - 2), *w1 = zslot(kc - 1), *w2 = zslot(kc), *w3 = zslot(kc + 1), *w4 = zslot(kc + 2);
     const bool z0 = wall && kc - 2 < 0, z1 = wall && kc - 1 < 0, z3 = wall && kc + 1 >= nz, z4 = wall && kc + 2 >= nz;
 #pragma unroll
@@ -166,8 +193,12 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
       if (v == idW) { if (z0) a0 = 0.0; if (z1) a1 = 0.0; if (z3) a3 = 0.0; if (z4) a4 = 0.0; }
       weno5_edges(a0, a1, a2, a3, a4, lo[v], hi[v]);
     }
-    p_lo = eos_pressure(lo[idT], __ldg(P.hyte + kc), __ldg(P.ihyte + kc), __ldg(P.pedge + kc), P);
-    p_hi = eos_pressure(hi[idT], __ldg(P.hyte + kc + 1), __ldg(P.ihyte + kc + 1), __ldg(P.pedge + kc + 1), P);
+    p_lo = eos_pressure_series(lo[idT], __ldg(P.ihyte + kc), __ldg(P.pedge + kc), P, big);
+    p_hi = eos_pressure_series(hi[idT], __ldg(P.ihyte + kc + 1), __ldg(P.pedge + kc + 1), P, big);
+  };
+  // |rt'/rt_bg| > 0.1 somewhere (never in the shipped cases): redo those pressures with the exact pow()
+  auto eos_repair = [&](double rtp, double bg, double &p) {
+    if (fabs(rtp) > 0.1 * bg) p = eos_pressure_slow(bg + rtp, P.C0, P.gamma);
   };
   auto store_flux_z = [&](const double (&f)[N], long long gface) {
     if (NT > 0 && in_dom) {
@@ -179,10 +210,12 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
   __syncthreads();                                           // barriers initialised
 
   // ---- prologue: level 0 in z and the bottom boundary face (DYC:1020-1038: both sides mirrored, w = 0 at a wall) ----
-  for (int lev = 0; lev < 3 && lev < nz; ++lev) mbar_wait_spin(&ibar[lev % NIS], 0u);
+  if (use_tma) for (int lev = 0; lev < 3 && lev < nz; ++lev) mbar_wait_spin(&ibar[lev % NIS], 0u);
   {
     double lo[N], hi[N], p_lo, p_hi;
-    zrecon(0, lo, hi, p_lo, p_hi);
+    int big = 0;
+    zrecon(0, lo, hi, p_lo, p_hi, big);
+    if (big) { eos_repair(lo[idT], __ldg(P.hyte), p_lo); eos_repair(hi[idT], __ldg(P.hyte + 1), p_hi); }
     double Lb[N];
 #pragma unroll
     for (int v = 0; v < N; ++v) Lb[v] = (v == idW && wall) ? 0.0 : lo[v];
@@ -205,24 +238,16 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     double prop = 0.0;
     if (P.use_immersed && in_dom) prop = __ldg(P.immersed + gcell);
 
-    mbar_wait_spin(&hbar[k % NHS], (uint32_t) ((k / NHS) & 1));
-    if (k + 3 < nz) mbar_wait_spin(&ibar[(k + 3) % NIS], (uint32_t) (((k + 3) / NIS) & 1));
+    if (use_tma) {
+      mbar_wait_spin(&hbar[k % NHS], (uint32_t) ((k / NHS) & 1));
+      if (k + 3 < nz) mbar_wait_spin(&ibar[(k + 3) % NIS], (uint32_t) (((k + 3) / NIS) & 1));
+    }
 
     // ================= phase 1: reconstructions =================
-    // ---- ring jobs ----
-#pragma unroll
-    for (int r = 0; r < C::NRND; ++r) {
-      const unsigned d = rj[r];
-      if (d & C::RJ_VALID) {
-        const double *q = Hk + (d & 0x1fffu);
-        const int st = (d & C::RJ_ISY) ? PX : 1;
-        double lo, hi;
-        weno5_edges(q[0], q[st], q[2 * st], q[3 * st], q[4 * st], lo, hi);
-        const double e = (d & C::RJ_HI) ? hi : lo;
-        sm[rj_dst[r]] = e;
-        if (d & C::RJ_IST) sm[rj_dst[r] + rj_pd[r]] = eos_pressure(e, hytc_k, ihytc_k, pcell_k, P);
-      }
-    }
+    // Straight-line code (two basic blocks): the equation of state is evaluated speculatively by its series (offenders are
+    // repaired below), ring jobs are predicated, the top boundary face is a select -- so that the scheduler can overlap the
+    // dependent chains (pressure series, single ring reconstructions, face flux) with the six-variable reconstructions.
+    int big = 0;
     // ---- y ----
     const double *Hc = Hk + hoff;
     double loy[N], hiy[N], p_loy = 0.0, p_hiy = 0.0;
@@ -232,11 +257,24 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
         const double *q = Hc + v * PLANE;
         weno5_edges(q[-2 * PX], q[-PX], q[0], q[PX], q[2 * PX], loy[v], hiy[v]);
       }
-      p_loy = eos_pressure(loy[idT], hytc_k, ihytc_k, pcell_k, P);
-      p_hiy = eos_pressure(hiy[idT], hytc_k, ihytc_k, pcell_k, P);
+      p_loy = eos_pressure_series(loy[idT], ihytc_k, pcell_k, P, big);
+      p_hiy = eos_pressure_series(hiy[idT], ihytc_k, pcell_k, P, big);
+    }
+    // ---- ring jobs: the (rho theta)' jobs are all in round 0 (NRC <= NTHR), whose pressure is evaluated by every thread ----
+    double ring_e[C::NRND], ring_p = 0.0;
 #pragma unroll
-      for (int v = 0; v < N; ++v) HY[(v * (TY + 1) + y + 1) * TX + x] = hiy[v];
-      HY[(N * (TY + 1) + y + 1) * TX + x] = p_hiy;
+    for (int r = 0; r < C::NRND; ++r) {
+      const unsigned d = rj[r];
+      const double *q = Hk + (d & 0x1fffu);
+      const int st = (d & C::RJ_ISY) ? PX : 1;
+      double lo, hi;
+      weno5_edges(q[0], q[st], q[2 * st], q[3 * st], q[4 * st], lo, hi);
+      ring_e[r] = (d & C::RJ_HI) ? hi : lo;
+      if (r == 0) {
+        int bigr = 0;
+        ring_p = eos_pressure_series(ring_e[0], ihytc_k, pcell_k, P, bigr);
+        if ((d & C::RJ_IST) && (d & C::RJ_VALID)) big |= bigr << 1;
+      }
     }
     // ---- x ----
     double lox[N], hix[N], p_lox, p_hix;
@@ -245,31 +283,55 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
       const double *q = Hc + v * PLANE;
       weno5_edges(q[-2], q[-1], q[0], q[1], q[2], lox[v], hix[v]);
     }
-    p_lox = eos_pressure(lox[idT], hytc_k, ihytc_k, pcell_k, P);
-    p_hix = eos_pressure(hix[idT], hytc_k, ihytc_k, pcell_k, P);
-    // ---- z: level k+1 and the flux through face k+1/2 ----
+    p_lox = eos_pressure_series(lox[idT], ihytc_k, pcell_k, P, big);
+    p_hix = eos_pressure_series(hix[idT], ihytc_k, pcell_k, P, big);
+    // ---- z: level k+1 (clamped to the top level: its values are replaced by the boundary state below) ----
+    const bool top = (k + 1 >= nz);
+    const int kz = top ? nz - 1 : k + 1;
+    double loz[N], hiz[N], p_loz, p_hiz;
+    zrecon(kz, loz, hiz, p_loz, p_hiz, big);
+    if (big) {                                               // rare: exact pressures where the series does not apply
+      eos_repair(loy[idT], hytc_k, p_loy); eos_repair(hiy[idT], hytc_k, p_hiy);
+      eos_repair(lox[idT], hytc_k, p_lox); eos_repair(hix[idT], hytc_k, p_hix);
+      eos_repair(loz[idT], __ldg(P.hyte + kz), p_loz); eos_repair(hiz[idT], __ldg(P.hyte + kz + 1), p_hiz);
+      if (big & 2) eos_repair(ring_e[0], hytc_k, ring_p);
+    }
+    // publish: y edge values of my cell, ring edge values
+    if (!sim2d) {
+#pragma unroll
+      for (int v = 0; v < N; ++v) HY[(v * (TY + 1) + y + 1) * TX + x] = hiy[v];
+      HY[(N * (TY + 1) + y + 1) * TX + x] = p_hiy;
+    }
+#pragma unroll
+    for (int r = 0; r < C::NRND; ++r) {
+      if (rj[r] & C::RJ_VALID) sm[rj_dst[r]] = ring_e[r];
+      if (r == 0 && (rj[0] & C::RJ_IST) && (rj[0] & C::RJ_VALID)) sm[rj_dst[0] + rj_pd[0]] = ring_p;
+    }
+    // flux through face k+1/2 (DYC:453-474); at the top boundary both sides are the mirrored interior state, w = 0 at a wall
     double fz_hi[N];
     {
       const double he = __ldg(P.hye + k + 1), hte = __ldg(P.hyte + k + 1);
-      if (k + 1 < nz) {
-        double loz[N], hiz[N], p_loz, p_hiz;
-        zrecon(k + 1, loz, hiz, p_loz, p_hiz);
-        face_flux<N, idW, true>(hiz_prev, loz, p_hiz_prev, p_loz, he, hte, fz_hi);
+      double Lz[N], Rz[N];
 #pragma unroll
-        for (int v = 0; v < N; ++v) hiz_prev[v] = hiz[v];
-        p_hiz_prev = p_hiz;
-      } else {                                               // top boundary face
-        double Lt[N];
-#pragma unroll
-        for (int v = 0; v < N; ++v) Lt[v] = (v == idW && wall) ? 0.0 : hiz_prev[v];
-        face_flux<N, idW, true>(Lt, Lt, p_hiz_prev, p_hiz_prev, he, hte, fz_hi);
+      for (int v = 0; v < N; ++v) {
+        Lz[v] = (top && v == idW && wall) ? 0.0 : hiz_prev[v];
+        Rz[v] = top ? Lz[v] : loz[v];
       }
+      face_flux<N, idW, true>(Lz, Rz, p_hiz_prev, top ? p_hiz_prev : p_loz, he, hte, fz_hi);
       store_flux_z(fz_hi, gcell + plane_cells);
+#pragma unroll
+      for (int v = 0; v < N; ++v) hiz_prev[v] = hiz[v];
+      p_hiz_prev = p_hiz;
     }
     __syncthreads();                                         // A: ring + y edge values published; planes k (haloed) and k-1 (interior) dead
-    if (tid == 0) {
-      if (k + NHS < nz) load_h(k + NHS);
-      if (k + 4 < nz) load_i(k + 4);
+    if (use_tma) {
+      if (tid == 0) {
+        if (k + NHS < nz) load_h(k + NHS);
+        if (k + 4 < nz) load_i(k + 4);
+      }
+    } else {
+      if (k + NHS < nz) plain_h(k + NHS);
+      if (k + 4 < nz) plain_i(k + 4);
     }
 
     // ================= phase 2: face fluxes =================
@@ -278,8 +340,8 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     {
       double L[N], pL, f_lo[N], f_hi[N];
 #pragma unroll
-      for (int v = 0; v < N; ++v) L[v] = shfl_up1(hix[v]);
-      pL = shfl_up1(p_hix);
+      for (int v = 0; v < N; ++v) L[v] = shfl_up1<TX>(hix[v]);
+      pL = shfl_up1<TX>(p_hix);
       if (x == 0) {
 #pragma unroll
         for (int v = 0; v < N; ++v) L[v] = sm[C::OFF_RXH + v * TY + y];
@@ -287,7 +349,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
       }
       face_flux<N, idU, false>(L, lox, pL, p_lox, hyc_k, hytc_k, f_lo);
 #pragma unroll
-      for (int v = 0; v < N; ++v) f_hi[v] = shfl_dn1(f_lo[v]);
+      for (int v = 0; v < N; ++v) f_hi[v] = shfl_dn1<TX>(f_lo[v]);
       if (x == TX - 1) {
         double R[N];
 #pragma unroll

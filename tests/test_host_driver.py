@@ -81,6 +81,7 @@ def test_reference_drivers_compile_unmodified(tmp_path, exp):
     build_driver()
     exe = str(tmp_path / ("ref_" + exp.split("/")[0]))
     cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-I", HOST, "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "tests", "stubs"),          # an include the surrogate driver names but never uses
            os.path.join(REF, "experiments", exp), "-o", exe, "-L", os.path.join(ROOT, "miniweatherml_b200"), "-lmwb200",
            "-Wl,-rpath," + os.path.join(ROOT, "miniweatherml_b200"), "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
