@@ -163,10 +163,15 @@ int  mw_mlp_forward(long long B, const float *weights /*host*/, const float *x, 
                     void *stream);
 
 /* general Dense(nin->nh) + LeakyReLU(negative_slope) + Dense(nh->nout) in fp32 with ponni's operation order (the model family
- * of ponni's own known-answer test, external/ponni/unit/keras_sequential/test_keras_sequential.cpp:11-50); widths <= 64.
+ * of ponni's own known-answer test, external/ponni/unit/keras_sequential/test_keras_sequential.cpp:11-50); widths <= 256.
  * weights: HOST W1[nin][nh], b1[nh], W2[nh][nout], b2[nout] (Keras "kernel:0" is [in][out]); x device [nin][B], y device [nout][B] */
 int  mw_mlp_dense2_forward(long long B, int nin, int nh, int nout, float negative_slope, const float *weights,
                            const float *x, float *y, void *stream);
+/* the same network on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators): nin <= 16, nh <= 256,
+ * nout <= 16; agrees with the fp32 path to ponni's test tolerance (1e-6), not bit for bit.  The `use_tensor_cores` flag of
+ * mw_mlp_forward / mw_surrogate_forward selects the same kernels for the 5 -> 10 -> 4 network (PON:177-202). */
+int  mw_mlp_dense2_forward_tc(long long B, int nin, int nh, int nout, float negative_slope, const float *weights,
+                              const float *x, float *y, void *stream);
 
 /* ---- the other calls of the canonical step loop ---------------------------------------------------------- */
 /* the surrogate module's per-step diagnostic (PON:258-269: sum(a - b) / size of nfields field pairs), reduced on the device */

@@ -7,7 +7,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmwb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["dycore.cu", "physics.cu", "surrogate.cu", "comm.cu", "init.cu", "runtime.cu", "simple_city.cu"]
+SOURCES = ["dycore.cu", "physics.cu", "surrogate.cu", "surrogate_tc.cu", "comm.cu", "init.cu", "runtime.cu", "simple_city.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
 ]
 

@@ -70,6 +70,7 @@ def lib():
         ("mw_surrogate_forward", [C.c_longlong, fp, dp, dp] + [vp] * 9 + [C.c_int, vp]),
         ("mw_mlp_forward", [C.c_longlong, fp, vp, vp, C.c_int, vp]),
         ("mw_mlp_dense2_forward", [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, fp, vp, vp, vp]),
+        ("mw_mlp_dense2_forward_tc", [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, fp, vp, vp, vp]),
         ("mw_sponge_layer", [C.c_int, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_longlong] + [C.c_double] * 4 + [vp, vp]),
         ("mw_column_average", [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_longlong, vp, vp, vp]),
         ("mw_nudge_to_column", [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_double, vp, vp, vp]),
@@ -270,14 +271,16 @@ def mlp_forward(weights, x, use_tensor_cores=False):
     return y
 
 
-def mlp_dense2_forward(weights, x, nh, nout, negative_slope=0.1):
-    """general Dense -> LeakyReLU -> Dense (fp32, ponni order); weights = W1[nin][nh], b1, W2[nh][nout], b2 flattened"""
+def mlp_dense2_forward(weights, x, nh, nout, negative_slope=0.1, use_tensor_cores=False):
+    """general Dense -> LeakyReLU -> Dense; weights = W1[nin][nh], b1, W2[nh][nout], b2 flattened.  fp32 in ponni's order,
+    or (use_tensor_cores) tcgen05 3xTF32 within 1e-6 of it"""
     import torch
     w = np.ascontiguousarray(weights, dtype=np.float32)
     nin, B = x.shape
     assert w.size == nin * nh + nh + nh * nout + nout and x.dtype == torch.float32
     y = torch.empty((nout, B), dtype=torch.float32, device=x.device)
-    _check(lib().mw_mlp_dense2_forward(B, nin, nh, nout, negative_slope, _fp(w), _ptr(x.contiguous()), _ptr(y), _stream()))
+    fn = lib().mw_mlp_dense2_forward_tc if use_tensor_cores else lib().mw_mlp_dense2_forward
+    _check(fn(B, nin, nh, nout, negative_slope, _fp(w), _ptr(x.contiguous()), _ptr(y), _stream()))
     return y
 
 

@@ -794,12 +794,12 @@ extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields
     for (int f = 0; f < h->N; ++f) MW_CUDA_OK(cudaMalloc(&h->dev_fields[f], bytes));
     h->dev_fields_alloc = true;
   }
-  // slab pipeline: single rank, 3-D, the warp-specialised stage kernel, and enough rows for >= 6 slabs of whole tile
-  // rows with about one wave of tiles (148 SMs, one CTA each) per slab launch.  MW_HOST_SLAB_ROWS overrides (0 = off).
+  // slab pipeline: 3-D, equal blocks, and enough rows for >= 4 slabs of whole tile rows with most of a wave of tiles
+  // (148 SMs, one CTA each) per slab launch.  MW_HOST_SLAB_ROWS overrides (0 = off).
   int rows_per_slab = 0;
   {
     const int nbx = (c.nx + TILE_X - 1) / TILE_X;
-    int tile_rows = std::max(1, 148 / nbx);
+    int tile_rows = std::max(1, (148 * 4 / 5) / nbx);      // ~0.8 wave of CTAs per slab launch (r02i sweep: 56 rows at nx = 512)
     rows_per_slab = 8 * tile_rows;
     const char *e = getenv("MW_HOST_SLAB_ROWS");
     if (e) rows_per_slab = (atoi(e) / 8) * 8;

@@ -10,12 +10,11 @@
 // Two arithmetic paths:
 //   fma  : plain fp32, accumulation in ponni's order with separate multiply and add roundings, so results are
 //          bit-identical to the reference's CPU build (g++ -O2 without FMA contraction).
-//   mma  : tensor cores (mma.sync.m16n8k8 TF32, fp32 accumulate). Inputs and weights are split into a TF32 head
-//          and tail (x = xh + xl) and three products are accumulated (xh*wh + xl*wh + xh*wl), which keeps the
-//          result within ponni's own 1e-6 test tolerance of the fp32 answer.  At widths 5/10/4 the tensor pipe is
-//          nowhere near the bound (the kernel is HBM-bound); the path exists because the north star asks for the
-//          dense contractions on tensor cores and so the utilisation can be measured.
+//   tc   : Blackwell tensor cores, tcgen05.mma kind::tf32 with TMEM accumulators (surrogate_tc.cu).  Inputs and weights
+//          are split into a TF32 head and tail (x = xh + xl) and three products are accumulated (xl*wh + xh*wl +
+//          xh*wh), which keeps the result within ponni's own 1e-6 test tolerance of the fp32 answer.
 #include "mw_common.cuh"
+#include "surrogate_tc.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
@@ -118,123 +117,30 @@ __global__ void __launch_bounds__(256) k_surrogate_fmav(const MlpWeights w, cons
   }
 }
 
-// ---- tensor-core path ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t f2tf32(float f) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
-  return r;
-}
-__device__ __forceinline__ void split_tf32(float f, uint32_t &hi, uint32_t &lo) {
-  hi = f2tf32(f);
-  lo = f2tf32(f - __uint_as_float(hi));
-}
-// D(16x8) += A(16x8, row) * B(8x8, col), TF32 inputs, fp32 accumulate
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
-                                     const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
-  mma_tf32(d, al, bh);      // small terms first
-  mma_tf32(d, ah, bl);
-  mma_tf32(d, ah, bh);
-}
-
-// One warp processes 16 samples per step.  A = samples x features (16 x 8, K padded), B = weights (K x N tiles of 8).
-// m16n8k8 fragment layout (PTX ISA): with g = lane/4, t = lane%4
-//   A: a0 (row g, col t), a1 (row g+8, col t), a2 (row g, col t+4), a3 (row g+8, col t+4)
-//   B: b0 (row t, col g), b1 (row t+4, col g)
-//   C: c0 (row g, col 2t), c1 (row g, col 2t+1), c2 (row g+8, col 2t), c3 (row g+8, col 2t+1)
-template <bool FULL>
-__global__ void __launch_bounds__(256) k_surrogate_mma(const MlpWeights w, const SurrogateParams S, const float *xin,
-                                                       float *yout) {
-  __shared__ float hs[8][16][17];                  // per warp: hidden activations 16 samples x 16 (10 used)
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  // weight fragments (head/tail), layer 1: K = 8 (5 used), N = 16 (10 used) -> two n-tiles; bias folded in afterwards
-  uint32_t b1h[2][2], b1l[2][2], b2h[2][2], b2l[2][2];
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-    const int col = nt * 8 + g;
-    const float v0 = (t < 5 && col < 10) ? w.W1[t][col] : 0.f;
-    const float v1 = (t + 4 < 5 && col < 10) ? w.W1[t + 4][col] : 0.f;
-    split_tf32(v0, b1h[nt][0], b1l[nt][0]);
-    split_tf32(v1, b1h[nt][1], b1l[nt][1]);
-  }
-  // layer 2: K = 16 (10 used) -> two k-tiles, N = 8 (4 used)
-#pragma unroll
-  for (int kt = 0; kt < 2; ++kt) {
-    const int r0 = kt * 8 + t, r1 = r0 + 4;
-    const float v0 = (r0 < 10 && g < 4) ? w.W2[r0][g] : 0.f;
-    const float v1 = (r1 < 10 && g < 4) ? w.W2[r1][g] : 0.f;
-    split_tf32(v0, b2h[kt][0], b2l[kt][0]);
-    split_tf32(v1, b2h[kt][1], b2l[kt][1]);
-  }
-  const long long nwarps = (long long) gridDim.x * (blockDim.x >> 5);
-  for (long long base = ((long long) blockIdx.x * (blockDim.x >> 5) + wrp) * 16; base < S.n; base += nwarps * 16) {
-    // A fragment: rows g and g+8 (samples), cols t and t+4 (features)
-    uint32_t ah[4], al[4];
-    const long long s0 = base + g, s1 = base + g + 8;
-    auto feat = [&](long long s, int f) -> float {
-      if (f >= 5 || s >= S.n) return 0.f;
-      if (FULL) return (float) ((S.in[f][s] - S.in_lo[f]) / (S.in_hi[f] - S.in_lo[f]));
-      return xin[f * S.n + s];
-    };
-    split_tf32(feat(s0, t), ah[0], al[0]);
-    split_tf32(feat(s1, t), ah[1], al[1]);
-    split_tf32(feat(s0, t + 4), ah[2], al[2]);
-    split_tf32(feat(s1, t + 4), ah[3], al[3]);
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
-      mma3(d, ah, al, b1h[nt], b1l[nt]);
-      const int c0 = nt * 8 + 2 * t;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int col = c0 + (q & 1), row = g + ((q >> 1) << 3);
-        float v = d[q] + (col < 10 ? w.b1[col] : 0.f);
-        if (v < 0.f) v *= 0.1f;
-        hs[wrp][row][col] = (col < 10) ? v : 0.f;
-      }
-    }
-    __syncwarp();
-    float d2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int kt = 0; kt < 2; ++kt) {
-      uint32_t hh[4], hl[4];
-      split_tf32(hs[wrp][g][kt * 8 + t], hh[0], hl[0]);
-      split_tf32(hs[wrp][g + 8][kt * 8 + t], hh[1], hl[1]);
-      split_tf32(hs[wrp][g][kt * 8 + t + 4], hh[2], hl[2]);
-      split_tf32(hs[wrp][g + 8][kt * 8 + t + 4], hh[3], hl[3]);
-      mma3(d2, hh, hl, b2h[kt], b2l[kt]);
-    }
-    __syncwarp();
-    // outputs: c0/c1 -> sample g, cols 2t, 2t+1 ; c2/c3 -> sample g+8 (only cols < 4 are real: t < 2)
-    if (t < 2) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int col = 2 * t + (q & 1);
-        const long long s = (q < 2) ? s0 : s1;
-        if (s < S.n) {
-          const float yv = d2[q] + w.b2[col];
-          if (FULL) {
-            const double v = (double) yv * S.out_rng[col] + S.out_lo[col];
-            S.out[col][s] = (col == 0) ? v : fmax(0.0, v);
-          } else {
-            yout[col * S.n + s] = yv;
-          }
-        }
-      }
-    }
-  }
-}
-
 static void fill_weights(MlpWeights &w, const float *p) {
   for (int i = 0; i < 5; ++i) for (int j = 0; j < 10; ++j) w.W1[i][j] = p[i * 10 + j];
   for (int j = 0; j < 10; ++j) w.b1[j] = p[50 + j];
   for (int i = 0; i < 10; ++i) for (int j = 0; j < 4; ++j) w.W2[i][j] = p[60 + i * 4 + j];
   for (int j = 0; j < 4; ++j) w.b2[j] = p[100 + j];
 }
+// the tensor-core kernels read the weights from global memory: a small per-call device copy (stream-ordered)
+struct DeviceWeights {
+  float *p = nullptr;
+  cudaStream_t st;
+  int upload(const float *host, size_t n, cudaStream_t s) {
+    st = s;
+    MW_CUDA_OK(cudaMallocAsync(&p, n * sizeof(float), st));
+    MW_CUDA_OK(cudaMemcpyAsync(p, host, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    return MW_OK;
+  }
+  int release() {                                   // `host` may be a pageable buffer of the caller: finish the copy first
+    if (!p) return MW_OK;
+    MW_CUDA_OK(cudaStreamSynchronize(st));
+    MW_CUDA_OK(cudaFreeAsync(p, st));
+    p = nullptr;
+    return MW_OK;
+  }
+};
 }  // namespace mw
 using namespace mw;
 
@@ -248,11 +154,15 @@ extern "C" int mw_mlp_forward(long long B, const float *weights, const float *x,
   fill_weights(w, weights);
   cudaStream_t st = (cudaStream_t) stream;
   if (use_tensor_cores) {
-    SurrogateParams S;
-    memset(&S, 0, sizeof(S));
-    S.n = B;
-    const unsigned grid = (unsigned) std::min<long long>((B + 127) / 128, 148 * 8);
-    k_surrogate_mma<false><<<grid, 256, 0, st>>>(w, S, x, y);
+    DeviceWeights dw;
+    rc = dw.upload(weights, 104, st);
+    if (rc != MW_OK) return rc;
+    TcParams T;
+    memset(&T, 0, sizeof(T));
+    T.B = B; T.nin = 5; T.nh = 10; T.nout = 4; T.slope = 0.1f; T.w = dw.p; T.x = x; T.y = y;
+    rc = launch_mlp_tc(T, false, st);
+    const int rc2 = dw.release();
+    return rc != MW_OK ? rc : rc2;
   } else {
     k_mlp_fma<<<(unsigned) ((B + 255) / 256), 256, 0, st>>>(w, x, y, B);
   }
@@ -279,8 +189,17 @@ extern "C" int mw_surrogate_forward(long long n, const float *weights, const dou
   for (int f = 0; f < 4; ++f) { S.out_lo[f] = scl_out[2 * f]; S.out_rng[f] = scl_out[2 * f + 1] - scl_out[2 * f]; }
   cudaStream_t st = (cudaStream_t) stream;
   if (use_tensor_cores) {
-    const unsigned grid = (unsigned) std::min<long long>((n + 127) / 128, 148 * 8);
-    k_surrogate_mma<true><<<grid, 256, 0, st>>>(w, S, nullptr, nullptr);
+    DeviceWeights dw;
+    rc = dw.upload(weights, 104, st);
+    if (rc != MW_OK) return rc;
+    TcParams T;
+    memset(&T, 0, sizeof(T));
+    T.B = n; T.nin = 5; T.nh = 10; T.nout = 4; T.slope = 0.1f; T.w = dw.p;
+    for (int f = 0; f < 5; ++f) { T.in[f] = S.in[f]; T.in_lo[f] = S.in_lo[f]; T.in_hi[f] = S.in_hi[f]; }
+    for (int f = 0; f < 4; ++f) { T.out[f] = S.out[f]; T.out_lo[f] = S.out_lo[f]; T.out_rng[f] = S.out_rng[f]; }
+    rc = launch_mlp_tc(T, true, st);
+    const int rc2 = dw.release();
+    return rc != MW_OK ? rc : rc2;
   } else {
     bool vec2 = (n % 2 == 0);
     for (int f = 0; f < 5; ++f) vec2 = vec2 && ((uintptr_t) S.in[f] % 16 == 0);
@@ -293,12 +212,12 @@ extern "C" int mw_surrogate_forward(long long n, const float *weights, const dou
   return MW_OK;
 }
 
-// ---- general Dense -> LeakyReLU -> Dense (any widths up to 64), fp32, ponni's operation order ------------------------
+// ---- general Dense -> LeakyReLU -> Dense (any widths up to 256), fp32, ponni's operation order -----------------------
 // The network family ponni's own known-answer test uses (external/ponni/unit/keras_sequential/test_keras_sequential.cpp:
 // 11-50: Dense(12->10) + LeakyReLU(0.1) + Dense(10->4), the 3-cell-stencil surrogate).  Weights sit in shared memory,
 // one thread per sample, hidden activations in registers.
 namespace mw {
-constexpr int MLP_MAXW = 64;
+constexpr int MLP_MAXW = 256;
 struct Dense2Params {
   const float *w;           // device: W1[nin][nh], b1[nh], W2[nh][nout], b2[nout]
   const float *x;           // [nin][B]
@@ -352,4 +271,25 @@ extern "C" int mw_mlp_dense2_forward(long long B, int nin, int nh, int nout, flo
   MW_CUDA_OK(cudaStreamSynchronize(st));                      // `weights` is a pageable host buffer of the caller
   MW_CUDA_OK(cudaFreeAsync(dw, st));
   return MW_OK;
+}
+
+// The same network on the tensor cores (tcgen05, 3xTF32; surrogate_tc.cu): nin <= 16, nh <= 256, nout <= 16.  Results
+// agree with mw_mlp_dense2_forward to ponni's 1e-6 test tolerance, not bit for bit.
+extern "C" int mw_mlp_dense2_forward_tc(long long B, int nin, int nh, int nout, float negative_slope, const float *weights,
+                                        const float *x, float *y, void *stream) {
+  int rc = device_check_cached();
+  if (rc != MW_OK) return rc;
+  MW_REQUIRE(weights && x && y && B >= 0, "mw_mlp_dense2_forward_tc: bad argument");
+  if (B == 0) return MW_OK;
+  const size_t nw = (size_t) nin * nh + nh + (size_t) nh * nout + nout;
+  cudaStream_t st = (cudaStream_t) stream;
+  DeviceWeights dw;
+  rc = dw.upload(weights, nw, st);
+  if (rc != MW_OK) return rc;
+  TcParams T;
+  memset(&T, 0, sizeof(T));
+  T.B = B; T.nin = nin; T.nh = nh; T.nout = nout; T.slope = negative_slope; T.w = dw.p; T.x = x; T.y = y;
+  rc = launch_mlp_tc(T, false, st);
+  const int rc2 = dw.release();
+  return rc != MW_OK ? rc : rc2;
 }

@@ -218,7 +218,35 @@ def test_mlp_dense2_vs_oracle(nin, nh, nout, B):
     y = mw.mlp_dense2_forward(w, torch.tensor(x, device="cuda"), nh, nout, 0.1).cpu().numpy()
     assert np.array_equal(y, O.mlp_dense2(w, x, nh, nout, 0.1))
     with pytest.raises(mw.MwError):
-        mw.mlp_dense2_forward(np.zeros(65 * 2 + 2 + 2 + 1, dtype=np.float32), torch.zeros((65, 4), device="cuda"), 2, 1)
+        mw.mlp_dense2_forward(np.zeros(257 * 2 + 2 + 2 + 1, dtype=np.float32), torch.zeros((257, 4), device="cuda"), 2, 1)
+
+
+@pytest.mark.parametrize("nin,nh,nout,B", [(12, 10, 4, 1000), (5, 10, 4, 257), (1, 1, 1, 3), (5, 64, 4, 4099), (16, 256, 16, 1000),
+                                           (3, 200, 7, 129), (8, 17, 16, 128)])
+def test_mlp_dense2_tensor_cores_vs_oracle(nin, nh, nout, B):
+    """tcgen05 path (3xTF32, TMEM accumulators) against the fp32 oracle: ponni's 1e-6 at the surrogate's size, the same
+    relative to the output magnitude for the wider layers of the width sweep (sums of up to 256 products)"""
+    import torch
+    import miniweatherml_b200 as mw
+    rng = np.random.default_rng(nin * 1000 + nh)
+    w = rng.uniform(-0.5, 0.5, nin * nh + nh + nh * nout + nout).astype(np.float32)
+    x = rng.uniform(-1, 1, (nin, B)).astype(np.float32)
+    ref = O.mlp_dense2(w, x, nh, nout, 0.1)
+    y = mw.mlp_dense2_forward(w, torch.tensor(x, device="cuda"), nh, nout, 0.1, use_tensor_cores=True).cpu().numpy()
+    assert np.isfinite(y).all()
+    assert np.abs(y - ref).max() <= 2e-6 * max(1.0, float(np.abs(ref).max())), np.abs(y - ref).max()
+    with pytest.raises(mw.MwError):
+        mw.mlp_dense2_forward(np.zeros(17 * 2 + 2 + 2 + 1, dtype=np.float32), torch.zeros((17, 4), device="cuda"), 2, 1,
+                              use_tensor_cores=True)
+
+
+def test_mlp_dense2_tensor_cores_keras_kat(golden):
+    """ponni's own known-answer test (test_keras_sequential.cpp:11-50) through the tensor-core path, at its own tolerance"""
+    import torch
+    import miniweatherml_b200 as mw
+    g = golden("keras_sequential_kat.npz")
+    y = mw.mlp_dense2_forward(g["w"], torch.tensor(g["x"], device="cuda"), 10, 4, 0.1, use_tensor_cores=True).cpu().numpy()
+    assert np.abs(y - g["y"]).max() <= float(g["tol"])
 
 
 @pytest.mark.parametrize("tc", [False, True])
