@@ -101,6 +101,10 @@ int  mw_dycore_get_background(mw_dycore *h, double *hy_dens_cells, double *hy_de
 /* installs (non-NULL) or removes (NULL) the immersed_proportion mask; use_immersed_boundaries follows it */
 int  mw_dycore_set_immersed(mw_dycore *h, const double *immersed_proportion /* device [nz][ny][nx] or NULL */);
 double mw_dycore_compute_time_step(const mw_dycore *h);
+/* the options compute_tendencies re-reads on every call (DYC:211-225: enable_gravity, grav, latitude, earthrot, C0, gamma_d,
+ * bc_z): forward their current coupler values before a step */
+int  mw_dycore_update_options(mw_dycore *h, int enable_gravity, double grav, double latitude, double earthrot, double C0,
+                              double gamma_d, int bc_z);
 /* fields: host array of 5+T DEVICE pointers in coupler order (density_dry,uvel,vvel,wvel,temp,tracers...) */
 int  mw_dycore_time_step(mw_dycore *h, double *const *fields, double dt_phys, void *stream);
 /* same through HOST buffers: H2D of the 5+T fields, the step, D2H of the results; synchronous */

@@ -87,6 +87,7 @@ def lib():
         ("mw_comm_destroy", [vp]),
         ("mw_comm_barrier", [vp]),
         ("mw_probe_fp64_rate", [dp]),
+        ("mw_dycore_update_options", [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
         ("mw_mean_difference", [C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_longlong, dp, vp]),
     ]:
         if hasattr(L, name):

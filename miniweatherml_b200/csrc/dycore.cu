@@ -278,6 +278,25 @@ extern "C" int mw_dycore_set_immersed(mw_dycore *h, const double *immersed) {
   return MW_OK;
 }
 
+// The reference re-reads these coupler options at every compute_tendencies call (DYC:211-225); the host module forwards
+// their current values before each step so that a set_option() after init() is honoured.
+extern "C" int mw_dycore_update_options(mw_dycore *h, int enable_gravity, double grav, double latitude, double earthrot,
+                                        double C0, double gamma_d, int bc_z) {
+  MW_REQUIRE(h, "mw_dycore_update_options: null handle");
+  MW_REQUIRE(bc_z == MW_BC_WALL || bc_z == MW_BC_OPEN, "bc_z must be wall or open");
+  MW_REQUIRE(C0 > 0 && gamma_d > 1, "mw_dycore_update_options: C0 = %g, gamma_d = %g", C0, gamma_d);
+  mw_config &c = h->cfg;
+  const bool eos_changed = (C0 != c.C0 || gamma_d != c.gamma_d);
+  c.enable_gravity = enable_gravity ? 1 : 0; c.grav = grav; c.latitude = latitude; c.earthrot = earthrot;
+  c.C0 = C0; c.gamma_d = gamma_d; c.bc_z = bc_z;
+  if (eos_changed && h->bg_set) {                          // the pressure tables depend on C0 and gamma
+    const int nz = c.nz;
+    const std::vector<double> bg = h->bg_host;
+    return mw_dycore_set_background(h, &bg[0], &bg[nz], &bg[2 * nz], &bg[3 * nz + 1]);
+  }
+  return MW_OK;
+}
+
 extern "C" double mw_dycore_compute_time_step(const mw_dycore *h) {      // DYC:70-77
   if (!h) return 0.0;
   const double maxwave = 350 + 80, cfl = 0.6;
@@ -383,7 +402,9 @@ static int exchange_mult(mw_dycore *h, cudaStream_t st) {
 
 // tracer finish (FCT-scaled divergence, RK, clip); with decomposed directions the neighbours' FCT factors come first
 static int exchange_halos(mw_dycore *h, double *q, cudaStream_t st);
-static int finish_stage_local(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st, bool mult_done = false) {
+// `Qd2c` (last stage of a step): the tracer finish also writes the coupler fields (k_tracer_update_d2c)
+static int finish_stage_local(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st, bool mult_done = false,
+                              const ConvertParams *Qd2c = nullptr) {
   if (nt > 0) {
     if (!mult_done) {
       int rc = exchange_mult(h, st);
@@ -391,11 +412,20 @@ static int finish_stage_local(mw_dycore *h, const StageParams &P, int nt, cudaSt
     }
     const long long ncell = (long long) P.nz * P.ny * P.nx;
     const unsigned g = (unsigned) ((ncell + 255) / 256);
-    switch (nt) {
-      case 1: k_tracer_update<1><<<g, 256, 0, st>>>(P); break;
-      case 2: k_tracer_update<2><<<g, 256, 0, st>>>(P); break;
-      case 3: k_tracer_update<3><<<g, 256, 0, st>>>(P); break;
-      case 4: k_tracer_update<4><<<g, 256, 0, st>>>(P); break;
+    if (Qd2c) {
+      switch (nt) {
+        case 1: k_tracer_update_d2c<1><<<g, 256, 0, st>>>(P, *Qd2c); break;
+        case 2: k_tracer_update_d2c<2><<<g, 256, 0, st>>>(P, *Qd2c); break;
+        case 3: k_tracer_update_d2c<3><<<g, 256, 0, st>>>(P, *Qd2c); break;
+        case 4: k_tracer_update_d2c<4><<<g, 256, 0, st>>>(P, *Qd2c); break;
+      }
+    } else {
+      switch (nt) {
+        case 1: k_tracer_update<1><<<g, 256, 0, st>>>(P); break;
+        case 2: k_tracer_update<2><<<g, 256, 0, st>>>(P); break;
+        case 3: k_tracer_update<3><<<g, 256, 0, st>>>(P); break;
+        case 4: k_tracer_update<4><<<g, 256, 0, st>>>(P); break;
+      }
     }
     MW_CUDA_OK(cudaGetLastError());
     h->launches++;
@@ -403,8 +433,8 @@ static int finish_stage_local(mw_dycore *h, const StageParams &P, int nt, cudaSt
   return MW_OK;
 }
 // ... followed by the halo exchange of the new state on the same stream (no overlap)
-static int finish_stage(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st) {
-  int rc = finish_stage_local(h, P, nt, st);
+static int finish_stage(mw_dycore *h, const StageParams &P, int nt, cudaStream_t st, const ConvertParams *Qd2c = nullptr) {
+  int rc = finish_stage_local(h, P, nt, st, false, Qd2c);
   if (rc != MW_OK) return rc;
   return exchange_halos(h, P.qout, st);
 }
@@ -433,7 +463,8 @@ template <int NT> struct StageKernel {
   }
 };
 template <int NT>
-static int launch_stage(mw_dycore *h, const StageParams &P0, int in_buf, cudaStream_t st, bool last) {
+static int launch_stage(mw_dycore *h, const StageParams &P0, int in_buf, cudaStream_t st, bool last,
+                        const ConvertParams *Qd2c = nullptr) {
   using K = StageKernel<NT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -477,8 +508,8 @@ static int launch_stage(mw_dycore *h, const StageParams &P0, int in_buf, cudaStr
   }
   MW_CUDA_OK(cudaGetLastError());
   if (h->timing) { cudaEventRecord(h->ev[3 + 2 * h->n_stage_timed], st); h->n_stage_timed++; }
-  if (!h->overlap) return finish_stage(h, P0, NT, st);
-  int rc = finish_stage_local(h, P0, NT, st, true);
+  if (!h->overlap) return finish_stage(h, P0, NT, st, Qd2c);
+  int rc = finish_stage_local(h, P0, NT, st, true, Qd2c);
   if (rc != MW_OK) return rc;
   return last ? MW_OK : exchange_halos_async(h, P0.qout, st);      // the last stage's halos are never read
 }
@@ -523,14 +554,18 @@ static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaSt
       else             { in_buf = 2; P.qout = h->q[0]; P.rk_a = 1. / 3.; P.rk_b = 2. / 3.; P.rk_cdt = (2. / 3.) * dt_dyn;   P.dt_stage = (2. / 3.) * dt_dyn; }
       P.qin = h->q[in_buf];
       P.q0 = h->q[0];
-      int rc = launch_stage<NT>(h, P, in_buf, st, ic == ncycles - 1 && s == 2);
+      const bool last = (ic == ncycles - 1 && s == 2);
+      // with tracers the last tracer finish also converts back to the coupler's variables (one launch and one pass less)
+      int rc = launch_stage<NT>(h, P, in_buf, st, last, (last && NT > 0) ? &Q : nullptr);
       if (rc != MW_OK) return rc;
     }
   }
-  Q.S.qin = h->q[0];
-  k_dyn_to_coupler<NT><<<cvgrid, 256, 0, st>>>(Q);
-  MW_CUDA_OK(cudaGetLastError());
-  h->launches++;
+  if (NT == 0) {
+    Q.S.qin = h->q[0];
+    k_dyn_to_coupler<NT><<<cvgrid, 256, 0, st>>>(Q);
+    MW_CUDA_OK(cudaGetLastError());
+    h->launches++;
+  }
   if (h->timing) cudaEventRecord(h->ev[1], st);
   return MW_OK;
 }
@@ -845,8 +880,12 @@ extern "C" int mw_dycore_attach_comm(mw_dycore *h, mw_comm *comm) {
   h->dir_active[0] = h->dir_active[1] = (c.nproc_x > 1);
   h->dir_active[2] = h->dir_active[3] = (c.nproc_y > 1) && !sim2d;
   {
-    const char *e = getenv("MW_NO_OVERLAP");
-    h->overlap = (h->dir_active[0] || h->dir_active[2]) && !(e && atoi(e) != 0);
+    // Exchange overlapped with the interior tiles (MW_OVERLAP=1) is off by default: a cell-kernel CTA takes a whole SM
+    // (254 registers x 256 threads), so the pack / NCCL / unpack kernels and the boundary tiles each wait for a CTA to
+    // retire (0.7 ms) and the boundary tiles end up as a tail -- measured 20.3 ms per step against 18.9 ms with the
+    // exchange simply following the stage on the same stream (2 GPUs, 512 x 512 x 128 per GPU, r02k).
+    const char *e = getenv("MW_OVERLAP");
+    h->overlap = (h->dir_active[0] || h->dir_active[2]) && e && atoi(e) != 0;
     if (h->overlap && !h->cs) {
       // high priority: the few boundary CTAs and the pack / NCCL / unpack kernels are dispatched ahead of the queued
       // interior CTAs as SMs free up, so they never form a tail of their own

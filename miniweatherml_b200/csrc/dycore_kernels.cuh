@@ -142,8 +142,19 @@ __device__ __forceinline__ void riemann(double pL, double pR, double mL, double 
 // Across the global periodic seam the donor's factor is NOT applied, which is what the reference does with its
 // two independent copies of that face.
 // --------------------------------------------------------------------------------------------------------
-template <int NT>
-__global__ void __launch_bounds__(256) k_tracer_update(const StageParams P) {
+struct ConvertParams {
+  StageParams S;                                   // geometry, profiles, constants (qout = dycore-form buffer)
+  double *fields[NUM_STATE + MW_MAX_TRACERS];      // coupler fields [nz][ny][nx]
+  double R_d, R_v;
+  int idWV;
+  unsigned adds_mass_mask;
+};
+
+// D2C = true (last stage of a step): the dycore -> coupler conversion of the cell (DYC:1891-1951, k_dyn_to_coupler below)
+// is done here as well, from the values this thread has just formed -- one pass over the state less per step.  The
+// arithmetic is the unfused one (concentration stored, then multiplied back), so both forms give the same bits.
+template <int NT, bool D2C>
+__device__ __forceinline__ void tracer_finish_cell(const StageParams &P, const ConvertParams *Qp) {
   const long long ncell = (long long) P.nz * P.ny * P.nx;
   int i, j, k;
   long long c;
@@ -151,6 +162,7 @@ __global__ void __launch_bounds__(256) k_tracer_update(const StageParams P) {
   const long long hcell = (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + i + HALO;
   const double rho_new = P.qout[hcell] + __ldg(P.hyc + k);
   const long long pl = (long long) P.ny * P.nx;
+  double tr_mass[NT > 0 ? NT : 1];
 #pragma unroll
   for (int tr = 0; tr < NT; ++tr) {
     const double *FXp = P.flux_x + (((long long) tr * P.nz + k) * P.ny + j) * (P.nx + 1) + i;
@@ -175,21 +187,39 @@ __global__ void __launch_bounds__(256) k_tracer_update(const StageParams P) {
     double *qv = P.qout + (long long) (NUM_STATE + tr) * P.vstride;
     double qn = qv[hcell] + P.rk_cdt * t;
     if ((P.positive_mask >> tr) & 1u) qn = fmax(0.0, qn);
-    store_with_images(qv, P, k, j, i, qn / rho_new);     // IEEE division: keeps the tracer-mass round trip unbiased
+    const double conc = qn / rho_new;                    // IEEE division: keeps the tracer-mass round trip unbiased
+    store_with_images(qv, P, k, j, i, conc);
+    if (D2C) tr_mass[tr] = conc * rho_new;
   }
+  if (D2C) {
+    const ConvertParams &Q = *Qp;
+    const double rt = P.qout[(long long) idT * P.vstride + hcell] + __ldg(P.hytc + k);
+    const double press = P.C0 * pow(rt, P.gamma);
+    double rho_d = rho_new, rho_v = 0.0;
+#pragma unroll
+    for (int tr = 0; tr < NT; ++tr) {
+      Q.fields[NUM_STATE + tr][c] = tr_mass[tr];
+      if ((Q.adds_mass_mask >> tr) & 1u) rho_d -= tr_mass[tr];
+      if (tr == Q.idWV) rho_v = tr_mass[tr];
+    }
+    Q.fields[0][c] = rho_d;
+    Q.fields[1][c] = P.qout[(long long) idU * P.vstride + hcell];
+    Q.fields[2][c] = P.qout[(long long) idV * P.vstride + hcell];
+    Q.fields[3][c] = P.qout[(long long) idW * P.vstride + hcell];
+    Q.fields[4][c] = press / (rho_d * Q.R_d + rho_v * Q.R_v);
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256) k_tracer_update(const StageParams P) { tracer_finish_cell<NT, false>(P, nullptr); }
+template <int NT>
+__global__ void __launch_bounds__(256) k_tracer_update_d2c(const StageParams P, const __grid_constant__ ConvertParams Q) {
+  tracer_finish_cell<NT, true>(P, &Q);
 }
 
 // --------------------------------------------------------------------------------------------------------
 // Coupler <-> dycore form (DYC:1955-2015 and DYC:1891-1951)
 // --------------------------------------------------------------------------------------------------------
-struct ConvertParams {
-  StageParams S;                                   // geometry, profiles, constants (qout = dycore-form buffer)
-  double *fields[NUM_STATE + MW_MAX_TRACERS];      // coupler fields [nz][ny][nx]
-  double R_d, R_v;
-  int idWV;
-  unsigned adds_mass_mask;
-};
-
 template <int NT>
 __global__ void __launch_bounds__(256) k_coupler_to_dyn(const ConvertParams Q) {
   const StageParams &P = Q.S;

@@ -161,7 +161,7 @@ __device__ __forceinline__ void kessler_adjust(double &theta, double &qv, double
 // before it is overwritten); consecutive threads take consecutive columns (coalesced).  The one value a thread needs
 // from ANOTHER thread's cells -- rho_r of the first level of the chunk above, which that thread updates in place --
 // is saved by the dtmin pass (bnd[chunk][col], 1/KES_LPT of a field).
-__global__ void __launch_bounds__(256) k_kessler_single(const KesslerParams K) {
+__global__ void __launch_bounds__(256, 3) k_kessler_single(const KesslerParams K) {
   if (*K.rainsplit != 1) return;
   const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   const long long nc = K.ncol, i = t % nc;

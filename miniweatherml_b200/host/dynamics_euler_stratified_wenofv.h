@@ -47,6 +47,15 @@ class Dynamics_Euler_Stratified_WenoFV {
     int const nens = coupler.get_nens();
     size_t const ncell = mw::member_cells(coupler);
     real const dt_in = dt_phys;
+    // DYC:211-225: these options are read at every step, so a set_option() after init() takes effect
+    mw::check(mw_dycore_update_options(handle, coupler.get_option<bool>("enable_gravity", true) ? 1 : 0, coupler.get_option<real>("grav"),
+                                       coupler.get_option<real>("latitude", 0.), coupler.get_option<real>("earthrot"),
+                                       coupler.get_option<real>("C0"), coupler.get_option<real>("gamma_d"),
+                                       coupler.get_option<int>("bc_z")), "mw_dycore_update_options");
+    if (coupler.get_option<bool>("use_immersed_boundaries", false) != (cfg.use_immersed_boundaries != 0)) {
+      update_immersed(coupler);
+      cfg.use_immersed_boundaries = coupler.get_option<bool>("use_immersed_boundaries", false) ? 1 : 0;
+    }
     bool const immersed = nens > 1 && coupler.get_option<bool>("use_immersed_boundaries", false);
     mw::for_each_member(field_ptrs, ncell, nens, true, [&](std::vector<double *> const &member, int iens) {   // DYC: every kernel loops iens
       if (immersed) {

@@ -18,7 +18,25 @@ from miniweatherml_b200 import distributed as mwd
 from test_gpu_dycore import synthetic_state
 
 
+def fixture_mode(names):
+    """mgpu_worker.py fixture <name> ...: the committed reference fixtures (single-rank reference runs) on the ranks' blocks;
+    building_city_loop6 = immersed boundaries + Horizontal_Sponge + sponge_layer across rank boundaries (simple_city loop)"""
+    from miniweatherml_b200.parity import fixture_parity
+    rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lrank)
+    dev = torch.device("cuda", lrank)
+    dist.init_process_group("nccl", device_id=dev)
+    comm = mwd.create_comm(dist, rank, world, dev)
+    res = [fixture_parity(dist, comm, rank, world, dev, n) for n in names]
+    if rank == 0:
+        print(json.dumps({"world": world, "checks": res, "ok": all(r["ok"] for r in res)}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "fixture":
+        return fixture_mode(sys.argv[2:])
     rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     nxg, nyg, T, steps = [int(a) for a in sys.argv[1:5]]
     physics = int(sys.argv[5]) if len(sys.argv) > 5 else 0

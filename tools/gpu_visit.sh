@@ -2,7 +2,7 @@
 # One parametrised GPU visit (replaces the per-visit scripts of round 1).
 #   usage: tools/gpu_visit.sh <tag> <step> [<step> ...]      outputs: gpurun_out/<tag>_*
 # steps: probe | tests_dycore | tests_physics | tests | variants | bench | bench_ref | launches | prof_stage | prof_kessler |
-#        physics | smoke | config3 | sass
+#        physics | smoke | config3 | multi | benchN | config3N (NGPU=2,4,8) | config3strong1
 # Env: VARIANTS (for `variants`, default "5 4"), BENCH_ARGS, PROF_KERNEL (regex for prof_stage, default k_stage)
 tag=$1; shift
 mkdir -p gpurun_out
@@ -26,6 +26,12 @@ for step in "$@"; do
                      python tools/probe_physics.py > ${o}_prof_kessler.log 2>&1; tail -2 ${o}_prof_kessler.log ;;
     physics)       timeout 600 python tools/probe_physics.py 2>&1 | tail -6 | tee ${o}_physics_probe.jsonl ;;
     smoke)         timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee ${o}_smoke.log ;;
+    multi)         timeout 1500 python -m pytest tests/test_gpu_multi.py tests/test_host_driver.py -m gpu -q --timeout 900 2>&1 | tail -12 | tee ${o}_tests_multi.log ;;
+    benchN)        timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29511 \
+                     bench.py --gpus $NGPU --steps 10 --warmup 3 2>>${o}_bench.err | tail -1 | tee ${o}_bench_n$NGPU.json ;;
+    config3N)      for sc in strong weak; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29512 \
+                     bench.py --gpus $NGPU --workload config3 --scaling $sc --steps 5 --warmup 3 --no-cpu-baseline 2>>${o}_bench.err | tail -1 | tee ${o}_bench_config3_${sc}_n$NGPU.json; done ;;
+    config3strong1) timeout 900 python bench.py --workload config3 --scaling strong --steps 3 --warmup 3 --no-cpu-baseline 2>>${o}_bench.err | tail -1 | tee ${o}_bench_config3_strong_n1.json ;;
     *) echo "unknown step $step" ;;
   esac
 done
