@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
         if p.wait() != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or procs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lnccl"]
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lnccl"]
         subprocess.check_call(cmd)
     return LIB
 

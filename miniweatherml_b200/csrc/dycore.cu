@@ -104,6 +104,20 @@ struct mw_dycore {
   int peer[4] = {0, 0, 0, 0};
   double *hsend[4] = {nullptr}, *hrecv[4] = {nullptr}, *msend[4] = {nullptr}, *mrecv[4] = {nullptr};
   size_t hcount[4] = {0}, mcount[4] = {0};
+  // Peer-memory halos (default for decomposed runs, MW_PEER_HALO=0 selects the NCCL exchange): the neighbours' RK
+  // registers, FCT-factor arrays and barrier flags mapped through CUDA IPC.  Kernels store the images of their edge cells
+  // straight into the neighbour's halo over NVLink; a flag barrier between neighbours replaces every exchange.
+  struct Peer {
+    double *q[3] = {nullptr, nullptr, nullptr};          // the neighbour's q0, q1, q2 (peer address space)
+    double *mult = nullptr;
+    unsigned long long *flags = nullptr;                   // the neighbour's flag array: I write slot (d ^ 1)
+    int nx = 0, ny = 0, pitch = 0;
+    long long zstride = 0, vstride = 0;
+  } peer_mem[4];
+  bool peer_halo = false;
+  unsigned long long *flags = nullptr;                     // my flag array [4]: slot d is written by the neighbour in direction d
+  unsigned long long epoch = 0;
+  std::vector<void *> ipc_opened;
   // halo exchange overlapped with interior compute: exchanges run on their own stream
   cudaStream_t cs = nullptr, cs2 = nullptr;                // exchange stream; second compute stream for the boundary tiles
   cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_prev = nullptr, ev_bnd = nullptr;
@@ -137,19 +151,54 @@ static StageParams base_params(const mw_dycore *h) {
   P.bc_z = c.bc_z;
   P.enable_gravity = c.enable_gravity;
   P.use_immersed = (c.use_immersed_boundaries && h->immersed) ? 1 : 0;
-  P.wrap_x = (c.nproc_x == 1);
-  P.wrap_y = (c.nproc_y == 1) && !P.sim2d;
   unsigned pm = 0;
   for (int t = 0; t < c.num_tracers; ++t) if (c.tracer_positive[t]) pm |= 1u << t;
   P.positive_mask = pm;
   P.use_tma = h->use_tma;
   P.tile_mode = 0;
   // FCT donors across interior rank boundaries (never across the global periodic seam, see StageParams)
-  P.mult_W = (h->dir_active[0] && c.px > 0) ? h->mrecv[0] : nullptr;
-  P.mult_E = (h->dir_active[1] && c.px < c.nproc_x - 1) ? h->mrecv[1] : nullptr;
-  P.mult_S = (h->dir_active[2] && c.py > 0) ? h->mrecv[2] : nullptr;
-  P.mult_N = (h->dir_active[3] && c.py < c.nproc_y - 1) ? h->mrecv[3] : nullptr;
+  const bool interior[4] = {h->dir_active[0] && c.px > 0, h->dir_active[1] && c.px < c.nproc_x - 1,
+                            h->dir_active[2] && c.py > 0, h->dir_active[3] && c.py < c.nproc_y - 1};
+  for (int d = 0; d < 4; ++d) {
+    StageParams::MultSrc &M = P.msrc[d];
+    if (!interior[d]) continue;
+    if (h->peer_halo) {                                    // the neighbour's own factor array [T][nz][ny'][nx']
+      const mw_dycore::Peer &R = h->peer_mem[d];
+      M.base = R.mult;
+      M.st_t = (long long) c.nz * R.ny * R.nx; M.st_k = (long long) R.ny * R.nx;
+      if (d < 2) { M.st_i = R.nx; M.off = (d == 0) ? R.nx - 1 : 0; }                         // W: its last column, E: its first
+      else       { M.st_i = 1;    M.off = (d == 2) ? (long long) (R.ny - 1) * R.nx : 0; }    // S: its last row,    N: its first
+    } else {                                               // packed strip received over NCCL: [T][nz][ny] or [T][nz][nx]
+      const long long len = (d < 2) ? c.ny : c.nx;
+      M.base = h->mrecv[d]; M.st_t = (long long) c.nz * len; M.st_k = len; M.st_i = 1; M.off = 0;
+    }
+  }
   return P;
+}
+
+// Destinations of the edge cells' images for a launch that writes RK register `buf` (StageParams::img): this rank's own
+// halo in a direction that is not decomposed (periodic wrap), the neighbour's halo in peer mode, nothing in NCCL mode.
+static void set_images(const mw_dycore *h, StageParams &P, int buf) {
+  const mw_config &c = h->cfg;
+  const bool sim2d = (c.ny_glob == 1);
+  for (int d = 0; d < 4; ++d) {
+    StageParams::ImgDst &D = P.img[d];
+    D.base = nullptr;
+    const bool decomposed = h->dir_active[d];
+    if (d >= 2 && sim2d) continue;
+    int nxr = c.nx, nyr = c.ny;                            // the receiver's block
+    if (!decomposed) { D.base = h->q[buf]; D.vstride = h->vstride; D.zstride = h->zstride; D.pitch = h->pitch; }
+    else if (h->peer_halo) {
+      const mw_dycore::Peer &R = h->peer_mem[d];
+      D.base = R.q[buf]; D.vstride = R.vstride; D.zstride = R.zstride; D.pitch = R.pitch; nxr = R.nx; nyr = R.ny;
+    } else continue;
+    // my cell (j, i) lands at row0 + j, col0 + i of the receiver's haloed array
+    D.row0 = HALO; D.col0 = HALO;
+    if (d == 0) D.col0 = nxr + HALO;                       // i in [0,3)        -> its east halo columns nx' + 3 + i
+    if (d == 1) D.col0 = HALO - c.nx;                      // i in [nx-3, nx)   -> its west halo columns i - nx + 3
+    if (d == 2) D.row0 = nyr + HALO;
+    if (d == 3) D.row0 = HALO - c.ny;
+  }
 }
 
 extern "C" const char *mw_last_error(void) { return g_last_error.c_str(); }
@@ -226,6 +275,8 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
 
 extern "C" int mw_dycore_destroy(mw_dycore *h) {
   if (!h) return MW_OK;
+  for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  cudaFree(h->flags);
   for (int b = 0; b < 3; ++b) cudaFree(h->q[b]);
   cudaFree(h->flux_x); cudaFree(h->flux_y); cudaFree(h->flux_z); cudaFree(h->mult); cudaFree(h->bg);
   if (h->dev_fields_alloc) for (int f = 0; f < h->N; ++f) cudaFree(h->dev_fields[f]);
@@ -347,8 +398,37 @@ static int exchange(mw_dycore *h, double *const *send, double *const *recv, cons
   return MW_OK;
 }
 
+// Neighbour barrier of the peer-memory mode: thread d tells the neighbour in direction d "everything I launched before this
+// on my stream is done and visible" (its stores into your halo included) and waits for the same word from it.  A lost
+// neighbour must fail loudly, not hang the GPU: trap after ~10 s of polling.
+__global__ void k_peer_barrier(unsigned long long *mine, unsigned long long *p0, unsigned long long *p1, unsigned long long *p2,
+                               unsigned long long *p3, unsigned long long epoch) {
+  unsigned long long *peer[4] = {p0, p1, p2, p3};
+  const int d = threadIdx.x;
+  if (d >= 4 || !peer[d]) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer[d] + (d ^ 1)), "l"(epoch) : "memory");
+  unsigned long long v = 0;
+  for (long long spin = 0;; ++spin) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + d) : "memory");
+    if (v >= epoch) break;
+    if (spin > (1ll << 26)) __trap();
+    __nanosleep(100);
+  }
+}
+static int peer_barrier(mw_dycore *h, cudaStream_t st) {
+  ++h->epoch;
+  unsigned long long *pf[4];
+  for (int d = 0; d < 4; ++d) pf[d] = h->dir_active[d] ? h->peer_mem[d].flags : nullptr;
+  k_peer_barrier<<<1, 32, 0, st>>>(h->flags, pf[0], pf[1], pf[2], pf[3], h->epoch);
+  MW_CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return MW_OK;
+}
+
 static int exchange_halos(mw_dycore *h, double *q, cudaStream_t st) {
   if (!h->dir_active[0] && !h->dir_active[2]) return MW_OK;
+  if (h->peer_halo) return peer_barrier(h, st);            // the producing kernels stored the halos themselves
   const mw_config &c = h->cfg;
   HaloParams H;
   H.nx = c.nx; H.ny = c.ny; H.nz = c.nz; H.nvar = h->N; H.pitch = h->pitch; H.zstride = h->zstride; H.vstride = h->vstride;
@@ -383,6 +463,7 @@ static int exchange_halos(mw_dycore *h, double *q, cudaStream_t st) {
 // boundary cells' FCT factors to the neighbouring ranks, between the stage kernel and the tracer finish
 static int exchange_mult(mw_dycore *h, cudaStream_t st) {
   if ((!h->dir_active[0] && !h->dir_active[2]) || h->cfg.num_tracers == 0) return MW_OK;
+  if (h->peer_halo) return peer_barrier(h, st);            // the tracer finish reads the neighbours' factor arrays directly
   const mw_config &c = h->cfg;
   MultEdgeParams M;
   M.nx = c.nx; M.ny = c.ny; M.nz = c.nz; M.nt = c.num_tracers; M.mult = h->mult;
@@ -533,6 +614,7 @@ static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaSt
   if (h->timing) { ensure_events(2); cudaEventRecord(h->ev[0], st); }
 
   Q.S.qout = h->q[0];
+  set_images(h, Q.S, 0);
   const unsigned cvgrid = (unsigned) ((ncell + 256 * CONV_CPT - 1) / (256 * CONV_CPT));      // CONV_CPT cells per thread
   k_coupler_to_dyn<NT><<<cvgrid, 256, 0, st>>>(Q);
   MW_CUDA_OK(cudaGetLastError());
@@ -554,6 +636,7 @@ static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaSt
       else             { in_buf = 2; P.qout = h->q[0]; P.rk_a = 1. / 3.; P.rk_b = 2. / 3.; P.rk_cdt = (2. / 3.) * dt_dyn;   P.dt_stage = (2. / 3.) * dt_dyn; }
       P.qin = h->q[in_buf];
       P.q0 = h->q[0];
+      set_images(h, P, (in_buf + 1) % 3);
       const bool last = (ic == ncycles - 1 && s == 2);
       // with tracers the last tracer finish also converts back to the coupler's variables (one launch and one pass less)
       int rc = launch_stage<NT>(h, P, in_buf, st, last, (last && NT > 0) ? &Q : nullptr);
@@ -736,6 +819,7 @@ static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double 
     if (lk.kind == 0) {
       ConvertParams q = Q;
       q.S.qout = h->q[0]; q.S.jr_lo = j0; q.S.jr_n = nj;
+      set_images(h, q.S, 0);
       k_coupler_to_dyn<NT><<<cvgrid, 256, 0, cs>>>(q);
     } else if (lk.kind == 3) {
       ConvertParams q = Q;
@@ -759,6 +843,7 @@ static int host_step_pipelined(mw_dycore *h, double *const *host_fields, double 
       else             { in_buf = 2; P.qout = h->q[0]; P.rk_a = 1. / 3.; P.rk_b = 2. / 3.; P.rk_cdt = (2. / 3.) * dt_dyn;   P.dt_stage = (2. / 3.) * dt_dyn; }
       P.qin = h->q[in_buf];
       P.q0 = h->q[0];
+      set_images(h, P, (in_buf + 1) % 3);
       if (lk.kind == 1 && tb > nby) {
         // seam: tile rows [ta, nby) and [0, tb - nby) = every tile outside the rectangle of rows [tb - nby, ta) (tile_mode 2)
         P.tile_mode = 2; P.nbx = nbx; P.nby = nby; P.tbx_lo = 0; P.tbx_hi = nbx; P.tby_lo = tb - nby; P.tby_hi = ta;
@@ -864,6 +949,64 @@ extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields
   return MW_OK;
 }
 
+// Map the neighbours' buffers (CUDA IPC; one process per GPU on one node).  Every rank publishes the handles of its three RK
+// registers, its FCT-factor array and its flag array plus its block geometry through one ncclAllGather; each rank opens
+// the handles of its (up to four, possibly coinciding) neighbours.
+namespace {
+struct PeerInfo {
+  cudaIpcMemHandle_t q[3], mult, flags;
+  int nx, ny, pitch, pad;
+  long long zstride, vstride;
+};
+}
+static int setup_peer_halos(mw_dycore *h) {
+  const mw_config &c = h->cfg;
+  const int nranks = c.nproc_x * c.nproc_y;
+  MW_CUDA_OK(cudaMalloc(&h->flags, 4 * sizeof(unsigned long long)));
+  MW_CUDA_OK(cudaMemset(h->flags, 0, 4 * sizeof(unsigned long long)));
+  PeerInfo mine;
+  memset(&mine, 0, sizeof(mine));
+  for (int b = 0; b < 3; ++b) MW_CUDA_OK(cudaIpcGetMemHandle(&mine.q[b], h->q[b]));
+  MW_CUDA_OK(cudaIpcGetMemHandle(&mine.mult, h->mult));
+  MW_CUDA_OK(cudaIpcGetMemHandle(&mine.flags, h->flags));
+  mine.nx = c.nx; mine.ny = c.ny; mine.pitch = h->pitch; mine.zstride = h->zstride; mine.vstride = h->vstride;
+  char *dsend = nullptr, *drecv = nullptr;
+  MW_CUDA_OK(cudaMalloc(&dsend, sizeof(PeerInfo)));
+  MW_CUDA_OK(cudaMalloc(&drecv, sizeof(PeerInfo) * nranks));
+  MW_CUDA_OK(cudaMemcpy(dsend, &mine, sizeof(PeerInfo), cudaMemcpyHostToDevice));
+  MW_NCCL_OK(ncclAllGather(dsend, drecv, sizeof(PeerInfo), ncclChar, h->comm->comm, 0));
+  std::vector<PeerInfo> all(nranks);
+  MW_CUDA_OK(cudaMemcpy(all.data(), drecv, sizeof(PeerInfo) * nranks, cudaMemcpyDeviceToHost));
+  cudaFree(dsend); cudaFree(drecv);
+  for (int d = 0; d < 4; ++d) {
+    if (!h->dir_active[d]) continue;
+    const int r = h->peer[d];
+    MW_REQUIRE(r != h->comm->rank, "peer halos: rank %d is its own neighbour in an active direction", r);
+    int prev = -1;
+    for (int e = 0; e < d; ++e) if (h->dir_active[e] && h->peer[e] == r) prev = e;
+    mw_dycore::Peer &R = h->peer_mem[d];
+    if (prev >= 0) { R = h->peer_mem[prev]; continue; }    // two ranks in a direction: both neighbours are the same process
+    const PeerInfo &I = all[r];
+    auto open = [&](const cudaIpcMemHandle_t &hd, void **out) -> cudaError_t {
+      cudaError_t e = cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess);
+      if (e == cudaSuccess) h->ipc_opened.push_back(*out);
+      return e;
+    };
+    for (int b = 0; b < 3; ++b) MW_CUDA_OK(open(I.q[b], (void **) &R.q[b]));
+    MW_CUDA_OK(open(I.mult, (void **) &R.mult));
+    MW_CUDA_OK(open(I.flags, (void **) &R.flags));
+    R.nx = I.nx; R.ny = I.ny; R.pitch = I.pitch; R.zstride = I.zstride; R.vstride = I.vstride;
+  }
+  // x neighbours share my rows, y neighbours my columns (block decomposition, CPL:147-153)
+  for (int d = 0; d < 4; ++d) {
+    if (!h->dir_active[d]) continue;
+    const mw_dycore::Peer &R = h->peer_mem[d];
+    MW_REQUIRE(d < 2 ? R.ny == c.ny : R.nx == c.nx, "peer halos: neighbour %d has a %d x %d block, mine is %d x %d", h->peer[d], R.nx, R.ny, c.nx, c.ny);
+  }
+  h->peer_halo = true;
+  return MW_OK;
+}
+
 extern "C" int mw_dycore_attach_comm(mw_dycore *h, mw_comm *comm) {
   MW_REQUIRE(h && comm, "mw_dycore_attach_comm: null argument");
   const mw_config &c = h->cfg;
@@ -896,6 +1039,14 @@ extern "C" int mw_dycore_attach_comm(mw_dycore *h, mw_comm *comm) {
       for (cudaEvent_t *e : {&h->ev_ready, &h->ev_halo, &h->ev_prev, &h->ev_bnd}) MW_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
   }
+  {
+    const char *e = getenv("MW_PEER_HALO");
+    if (!(e && atoi(e) == 0) && (h->dir_active[0] || h->dir_active[2])) {
+      int rc = setup_peer_halos(h);
+      if (rc != MW_OK) return rc;
+    }
+  }
+  if (h->peer_halo) { h->overlap = false; return MW_OK; }
   const size_t T = c.num_tracers;
   for (int d = 0; d < 4; ++d) {
     if (!h->dir_active[d]) continue;

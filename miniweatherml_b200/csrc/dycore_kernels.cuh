@@ -36,11 +36,18 @@ struct StageParams {
   double rk_a, rk_b, rk_cdt; // q_new = rk_a*q0 + rk_b*q + rk_cdt*L(q)
   double dt_stage;           // the dt handed to compute_tendencies (FCT and immersed time scale), DYC:119,136,157
   int sim2d, bc_z, enable_gravity, use_immersed;
-  int wrap_x, wrap_y;        // write periodic images into the halo (single rank in that direction)
-  // FCT factors of the neighbouring rank's boundary cells ([T][nz][ny] for W/E, [T][nz][nx] for S/N); nullptr where
-  // the local boundary is the global periodic seam (or the only rank in that direction): factor 1 there, which is
-  // what the reference does with its two copies of a seam face (DYC:508-509)
-  const double *mult_W, *mult_E, *mult_S, *mult_N;
+  // Where the images of my edge cells go: img[0] takes the cells with i < 3 (into the east halo of the west neighbour),
+  // img[1] those with i >= nx-3 (west halo of the east neighbour), img[2] / img[3] the same for j (south / north).  The
+  // neighbour is this rank itself in a direction that is not decomposed (periodic wrap), else the neighbour rank's buffer
+  // mapped through CUDA IPC: the producing kernel stores straight into peer memory over NVLink (no pack / send / unpack).
+  // base == nullptr: nobody to write to (NCCL exchange mode fills that halo).  Image of cell (l, k, j, i):
+  //   base + l*vstride + k*zstride + (row0 + j)*pitch + (col0 + i)
+  struct ImgDst { double *base; long long vstride, zstride; int pitch, row0, col0; } img[4];
+  // FCT factors of the neighbouring rank's boundary cells, W / E / S / N: value(tr, k, idx) = base[tr*st_t + k*st_k +
+  // idx*st_i + off], idx = j for W / E and i for S / N.  Either a packed strip received over NCCL or the neighbour's own
+  // factor array (peer memory).  base == nullptr where the local boundary is the global periodic seam (or the only rank
+  // in that direction): factor 1 there, which is what the reference does with its two copies of a seam face (DYC:508-509)
+  struct MultSrc { const double *base; long long st_t, st_k, st_i, off; } msrc[4];
   unsigned positive_mask;    // bit tr set <=> tracer tr must stay non-negative
   int use_tma;
   // which tiles a launch covers (halo exchange overlapped with interior compute): 0 = all (2-D grid), 1 = the interior
@@ -88,18 +95,33 @@ __device__ __forceinline__ bool range_cell(const StageParams &P, int &k, int &j,
 // the conversion kernels handle CELLS_PER_THREAD cells a thread, a grid's worth of threads apart (coalescing unchanged),
 // with all loads issued first: twice the bytes in flight per thread for kernels that otherwise wait on memory
 constexpr int CONV_CPT = 2;
-__device__ __forceinline__ void store_with_images(double *var_base, const StageParams &P, int k, int j, int i,
-                                                  double v) {
-  double *row = var_base + (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + HALO;
-  row[i] = v;
-  if (P.wrap_x) {
-    if (i < HALO) row[i + P.nx] = v;
-    if (i >= P.nx - HALO) row[i - P.nx] = v;
-  }
-  if (P.wrap_y) {
-    if (j < HALO) row[i + (long long) P.ny * P.pitch] = v;
-    if (j >= P.ny - HALO) row[i - (long long) P.ny * P.pitch] = v;
-  }
+// which image destinations cell (j, i) has: bit d set <=> P.img[d] takes it
+__device__ __forceinline__ int image_mask(const StageParams &P, int j, int i) {
+  int m = 0;
+  if (i < HALO && P.img[0].base) m |= 1;
+  if (i >= P.nx - HALO && P.img[1].base) m |= 2;
+  if (j < HALO && P.img[2].base) m |= 4;
+  if (j >= P.ny - HALO && P.img[3].base) m |= 8;
+  return m;
+}
+__device__ __forceinline__ void store_image(const StageParams &P, int d, int l, int k, int j, int i, double v) {
+  const StageParams::ImgDst &D = P.img[d];
+  D.base[(long long) l * D.vstride + (long long) k * D.zstride + (long long) (D.row0 + j) * D.pitch + (D.col0 + i)] = v;
+}
+__device__ __forceinline__ void store_images(const StageParams &P, int mask, int l, int k, int j, int i, double v) {
+  if (mask & 1) store_image(P, 0, l, k, j, i, v);
+  if (mask & 2) store_image(P, 1, l, k, j, i, v);
+  if (mask & 4) store_image(P, 2, l, k, j, i, v);
+  if (mask & 8) store_image(P, 3, l, k, j, i, v);
+}
+__device__ __forceinline__ void store_with_images(const StageParams &P, int l, int k, int j, int i, double v) {
+  P.qout[(long long) l * P.vstride + (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + HALO + i] = v;
+  const int m = image_mask(P, j, i);
+  if (m) store_images(P, m, l, k, j, i, v);
+}
+__device__ __forceinline__ double neighbour_mult(const StageParams &P, int d, int tr, int k, int idx) {
+  const StageParams::MultSrc &M = P.msrc[d];
+  return M.base[(long long) tr * M.st_t + (long long) k * M.st_k + (long long) idx * M.st_i + M.off];
 }
 
 // p = C0 * rt^gamma  (DYC:401).  rt = bg + rtp with |rtp/bg| of a few percent in every shipped test case, so
@@ -175,20 +197,18 @@ __device__ __forceinline__ void tracer_finish_cell(const StageParams &P, const C
     }
     if ((P.positive_mask >> tr) & 1u) {
       const double ms = Mp[0];
-      const long long eW = ((long long) tr * P.nz + k) * P.ny + j, eS = ((long long) tr * P.nz + k) * P.nx + i;
-      if (fxl > 0) { if (i > 0) fxl *= Mp[-1]; else if (P.mult_W) fxl *= P.mult_W[eW]; }             else if (fxl < 0) fxl *= ms;
-      if (fxh < 0) { if (i < P.nx - 1) fxh *= Mp[1]; else if (P.mult_E) fxh *= P.mult_E[eW]; }       else if (fxh > 0) fxh *= ms;
-      if (fyl > 0) { if (j > 0) fyl *= Mp[-P.nx]; else if (P.mult_S) fyl *= P.mult_S[eS]; }          else if (fyl < 0) fyl *= ms;
-      if (fyh < 0) { if (j < P.ny - 1) fyh *= Mp[P.nx]; else if (P.mult_N) fyh *= P.mult_N[eS]; }    else if (fyh > 0) fyh *= ms;
+      if (fxl > 0) { if (i > 0) fxl *= Mp[-1]; else if (P.msrc[0].base) fxl *= neighbour_mult(P, 0, tr, k, j); }             else if (fxl < 0) fxl *= ms;
+      if (fxh < 0) { if (i < P.nx - 1) fxh *= Mp[1]; else if (P.msrc[1].base) fxh *= neighbour_mult(P, 1, tr, k, j); }       else if (fxh > 0) fxh *= ms;
+      if (fyl > 0) { if (j > 0) fyl *= Mp[-P.nx]; else if (P.msrc[2].base) fyl *= neighbour_mult(P, 2, tr, k, i); }          else if (fyl < 0) fyl *= ms;
+      if (fyh < 0) { if (j < P.ny - 1) fyh *= Mp[P.nx]; else if (P.msrc[3].base) fyh *= neighbour_mult(P, 3, tr, k, i); }    else if (fyh > 0) fyh *= ms;
       if (fzl > 0) { if (k > 0) fzl *= Mp[-pl]; }                else if (fzl < 0) fzl *= ms;
       if (fzh < 0) { if (k < P.nz - 1) fzh *= Mp[pl]; }          else if (fzh > 0) fzh *= ms;
     }
     const double t = -(fxh - fxl) * P.rdx - (fyh - fyl) * P.rdy - (fzh - fzl) * P.rdz;
-    double *qv = P.qout + (long long) (NUM_STATE + tr) * P.vstride;
-    double qn = qv[hcell] + P.rk_cdt * t;
+    double qn = P.qout[(long long) (NUM_STATE + tr) * P.vstride + hcell] + P.rk_cdt * t;
     if ((P.positive_mask >> tr) & 1u) qn = fmax(0.0, qn);
     const double conc = qn / rho_new;                    // IEEE division: keeps the tracer-mass round trip unbiased
-    store_with_images(qv, P, k, j, i, conc);
+    store_with_images(P, NUM_STATE + tr, k, j, i, conc);
     if (D2C) tr_mass[tr] = conc * rho_new;
   }
   if (D2C) {
@@ -251,15 +271,15 @@ __global__ void __launch_bounds__(256) k_coupler_to_dyn(const ConvertParams Q) {
     for (int tr = 0; tr < NT; ++tr) if (tr == Q.idWV) rho_v = trv[u][tr];
     const double press = rho_d * Q.R_d * temp + rho_v * Q.R_v * temp;
     const double rt = pow(press / P.C0, 1.0 / P.gamma);          // rho*theta
-    store_with_images(P.qout + (long long) idR * P.vstride, P, k[u], j[u], i[u], rho - __ldg(P.hyc + k[u]));
-    store_with_images(P.qout + (long long) idU * P.vstride, P, k[u], j[u], i[u], f5[u][1]);
-    store_with_images(P.qout + (long long) idV * P.vstride, P, k[u], j[u], i[u], f5[u][2]);
-    store_with_images(P.qout + (long long) idW * P.vstride, P, k[u], j[u], i[u], f5[u][3]);
-    store_with_images(P.qout + (long long) idT * P.vstride, P, k[u], j[u], i[u], rt - __ldg(P.hytc + k[u]));
+    store_with_images(P, idR, k[u], j[u], i[u], rho - __ldg(P.hyc + k[u]));
+    store_with_images(P, idU, k[u], j[u], i[u], f5[u][1]);
+    store_with_images(P, idV, k[u], j[u], i[u], f5[u][2]);
+    store_with_images(P, idW, k[u], j[u], i[u], f5[u][3]);
+    store_with_images(P, idT, k[u], j[u], i[u], rt - __ldg(P.hytc + k[u]));
     const double r = 1.0 / rho;
 #pragma unroll
     for (int tr = 0; tr < NT; ++tr)
-      store_with_images(P.qout + (long long) (NUM_STATE + tr) * P.vstride, P, k[u], j[u], i[u], trv[u][tr] * r);
+      store_with_images(P, NUM_STATE + tr, k[u], j[u], i[u], trv[u][tr] * r);
   }
 }
 

@@ -166,11 +166,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
   // ---- running offsets ----------------------------------------------------------------------------------------------
   long long hcell = (long long) (min(gj, P.ny - 1) + HALO) * P.pitch + (min(gi, P.nx - 1) + HALO);   // haloed arrays
   long long gcell = (long long) min(gj, P.ny - 1) * P.nx + min(gi, P.nx - 1);                         // plain arrays
-  int img = 0;                                               // periodic images I write: bit0 +nx, bit1 -nx, bit2 +ny rows, bit3 -ny rows
-  if (P.wrap_x) img |= (gi < HALO ? 1 : 0) | (gi >= P.nx - HALO ? 2 : 0);
-  if (P.wrap_y) img |= (gj < HALO ? 4 : 0) | (gj >= P.ny - HALO ? 8 : 0);
-  if (!in_dom) img = 0;
-  const long long yimg = (long long) P.ny * P.pitch;
+  const int img = in_dom ? image_mask(P, gj, gi) : 0;       // images of my cell: periodic wrap or a neighbour rank's halo (peer memory)
   const bool have_q0 = P.rk_a != 0.0;
   const int hoff = (y + HALO) * PX + (x + HALO);             // my cell in a haloed plane slot
   double *HY = sm + C::OFF_HY, *FY = sm + C::OFF_FY;
@@ -444,12 +440,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
               out = (l == idT) ? qn : qn * r_new;
             }
             qo[0] = out;
-            if (img) {
-              if (img & 1) qo[P.nx] = out;
-              if (img & 2) qo[-P.nx] = out;
-              if (img & 4) qo[yimg] = out;
-              if (img & 8) qo[-yimg] = out;
-            }
+            if (img) store_images(P, img, l, k, gj, gi, out);
           } else {
             // tracer: leave the RK base value in qout and the FCT factor in mult for k_tracer_update
             const int tr = l - NUM_STATE;

@@ -20,9 +20,11 @@ def decomposition(nranks, rank, sim2d=False):
 
 def block_range(n_glob, nproc, p):
     """i_beg, n_local as in model/core/coupler.h:147-153 (round(nper*p) .. round(nper*(p+1))-1)."""
+    import math
     nper = float(n_glob) / nproc
-    beg = int(round(nper * p))
-    end = int(round(nper * (p + 1))) - 1
+    rnd = lambda v: int(math.floor(v + 0.5))        # C++ round(): halves away from zero (Python's round() goes to even)
+    beg = rnd(nper * p)
+    end = rnd(nper * (p + 1)) - 1
     return beg, end - beg + 1
 
 

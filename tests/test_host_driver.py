@@ -143,7 +143,7 @@ def test_host_driver_two_ranks_matches_reference_fixture(tmp_path):
     # 2 ranks on a 3-D grid: 1 x 2 decomposition (split in y), blocks by round(nper*p) (CPL:147-153)
     j0 = 0
     for r in range(2):
-        jb, je = int(round(ny / 2 * r)), int(round(ny / 2 * (r + 1)))
+        jb, je = int(np.floor(ny / 2 * r + 0.5)), int(np.floor(ny / 2 * (r + 1) + 0.5))
         raw = np.fromfile(dump + ".%d" % r)
         out[:, :, jb:je, :] = raw[:nf * nz * (je - jb) * nx].reshape(nf, nz, je - jb, nx)
     _compare(out, g["s1"])

@@ -25,18 +25,19 @@ def ref_decomp(nranks, ny_glob, nx_glob):
             npy -= 1
         npx = nranks // npy
     out = []
+    cround = lambda v: int(math.floor(v + 0.5))      # C++ round() (CPL:147-153), not Python's round-half-to-even
     for r in range(nranks):
         py, px = r // npx, r % npx
         nper = nx_glob / npx
-        ib, ie = int(round(nper * px)), int(round(nper * (px + 1))) - 1
+        ib, ie = cround(nper * px), cround(nper * (px + 1)) - 1
         nper = ny_glob / npy
-        jb, je = int(round(nper * py)), int(round(nper * (py + 1))) - 1
+        jb, je = cround(nper * py), cround(nper * (py + 1)) - 1
         out.append((npx, npy, px, py, ib, ie, jb, je))
     return out
 
 
 @pytest.mark.parametrize("nranks", [1, 2, 3, 4, 6, 8])
-@pytest.mark.parametrize("grid", [(100, 1), (512, 512), (2048, 2048), (37, 19)])
+@pytest.mark.parametrize("grid", [(100, 1), (512, 512), (2048, 2048), (37, 19), (50, 50)])
 def test_decomposition_matches_reference_formula(nranks, grid):
     from miniweatherml_b200 import distributed as mwd
     nxg, nyg = grid
