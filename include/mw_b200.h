@@ -59,7 +59,7 @@ typedef struct {
   double R_d, R_v, cp_d, p0, grav;    /* options set by micro/dycore init (KES:85-94, DYC:1227-1232)               */
   double C0, gamma_d;                 /* DYC:1242-1247                                                             */
   double earthrot, latitude;          /* fcor = 2*earthrot*sin(latitude) (DYC:213)                                 */
-  int    bc_x, bc_y, bc_z;            /* only periodic x/y are implemented; bc_z wall or open                      */
+  int    bc_x, bc_y, bc_z;            /* x, y: periodic, open or wall; bc_z: wall or open (periodic z is not implemented) */
   int    enable_gravity;
   int    use_immersed_boundaries;
 } mw_config;
@@ -105,6 +105,11 @@ double mw_dycore_compute_time_step(const mw_dycore *h);
  * bc_z): forward their current coupler values before a step */
 int  mw_dycore_update_options(mw_dycore *h, int enable_gravity, double grav, double latitude, double earthrot, double C0,
                               double gamma_d, int bc_z);
+/* bc_x / bc_y are read at every halo and edge exchange (DYC:588-589, :846-847): periodic, open or wall.  Open / wall:
+ * the halo of a domain boundary repeats the edge cell and the boundary face sees its inner state on both sides, normal
+ * velocity zero at a wall (DYC:782-825, :1040-1080).  With ONE rank in a direction the reference applies the face condition
+ * to the west / south face only (`else if`, DYC:1051, :1072) and so does this library; with two or more ranks both get it. */
+int  mw_dycore_update_lateral_bc(mw_dycore *h, int bc_x, int bc_y);
 /* fields: host array of 5+T DEVICE pointers in coupler order (density_dry,uvel,vvel,wvel,temp,tracers...) */
 int  mw_dycore_time_step(mw_dycore *h, double *const *fields, double dt_phys, void *stream);
 /* same through HOST buffers: H2D of the 5+T fields, the step, D2H of the results; synchronous */

@@ -88,6 +88,7 @@ def lib():
         ("mw_comm_barrier", [vp]),
         ("mw_probe_fp64_rate", [dp]),
         ("mw_dycore_update_options", [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
+        ("mw_dycore_update_lateral_bc", [vp, C.c_int, C.c_int]),
         ("mw_mean_difference", [C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_longlong, dp, vp]),
     ]:
         if hasattr(L, name):
@@ -121,7 +122,7 @@ def _stream():
 
 def make_config(nx, ny, nz, xlen, ylen, zlen, num_tracers, idWV=0, positive=None, adds_mass=None, bc_z=BC_WALL,
                 use_immersed=False, enable_gravity=True, nx_glob=None, ny_glob=None, i_beg=0, j_beg=0, nproc_x=1,
-                nproc_y=1, px=0, py=0, latitude=0.0):
+                nproc_y=1, px=0, py=0, latitude=0.0, bc_x=BC_PERIODIC, bc_y=BC_PERIODIC):
     """Same defaults the reference ends up with for its shipped test cases (KES:85-94, DYC:1227-1249,1332-1335)."""
     cfg = Config()
     cfg.nx, cfg.ny, cfg.nz, cfg.nens = nx, ny, nz, 1
@@ -134,7 +135,7 @@ def make_config(nx, ny, nz, xlen, ylen, zlen, num_tracers, idWV=0, positive=None
         cfg.tracer_positive[t] = 1 if positive is None else int(positive[t])
         cfg.tracer_adds_mass[t] = 1 if adds_mass is None else int(adds_mass[t])
     cfg.latitude = latitude
-    cfg.bc_x, cfg.bc_y, cfg.bc_z = BC_PERIODIC, BC_PERIODIC, bc_z
+    cfg.bc_x, cfg.bc_y, cfg.bc_z = bc_x, bc_y, bc_z
     cfg.enable_gravity = 1 if enable_gravity else 0
     cfg.use_immersed_boundaries = 1 if use_immersed else 0
     _check(lib().mw_config_defaults(C.byref(cfg)))

@@ -96,6 +96,7 @@ struct mw_dycore {
   mw_comm *comm = nullptr;
   long long launches = 0;
   int use_tma = 1;
+  bool bc_both_faces = false;          // MW_BC_BOTH_FACES=1, see base_params
   // staging for the *_host entry point
   double *dev_fields[NUM_STATE + MW_MAX_TRACERS] = {nullptr};
   bool dev_fields_alloc = false;
@@ -131,6 +132,17 @@ struct mw_dycore {
   int n_stage_timed = 0;
 };
 
+// Open / wall lateral boundary on side d (W, E, S, N) of THIS rank's block: the boundary-condition code, else 0
+// (periodic direction, interior rank boundary, 2-D run in y).  DYC:782-825 tests px / py the same way.
+static int bc_side(const mw_dycore *h, int d) {
+  const mw_config &c = h->cfg;
+  if (d >= 2 && c.ny_glob == 1) return 0;
+  const int bc = d < 2 ? c.bc_x : c.bc_y;
+  if (bc != MW_BC_OPEN && bc != MW_BC_WALL) return 0;
+  const int p = d < 2 ? c.px : c.py, np = d < 2 ? c.nproc_x : c.nproc_y;
+  return ((d & 1) ? p == np - 1 : p == 0) ? bc : 0;
+}
+
 static StageParams base_params(const mw_dycore *h) {
   StageParams P;
   memset(&P, 0, sizeof(P));
@@ -156,6 +168,14 @@ static StageParams base_params(const mw_dycore *h) {
   P.positive_mask = pm;
   P.use_tma = h->use_tma;
   P.tile_mode = 0;
+  for (int d = 0; d < 4; ++d) {
+    P.hbc[d] = P.fbc[d] = bc_side(h, d);
+    // one rank in the direction: the reference applies the boundary condition to the low FACE only (DYC:1051, :1072
+    // `else if`) and the high one keeps the periodic neighbour's outer state; MW_BC_BOTH_FACES=1 gives the
+    // two-or-more-ranks behaviour on one rank (tests)
+    if ((d & 1) && P.fbc[d] && (d < 2 ? c.nproc_x : c.nproc_y) == 1 && !h->bc_both_faces) P.fbc[d] = MW_FBC_REF1;
+    if (P.hbc[d]) P.bc_any = 1;
+  }
   // FCT donors across interior rank boundaries (never across the global periodic seam, see StageParams)
   const bool interior[4] = {h->dir_active[0] && c.px > 0, h->dir_active[1] && c.px < c.nproc_x - 1,
                             h->dir_active[2] && c.py > 0, h->dir_active[3] && c.py < c.nproc_y - 1};
@@ -186,6 +206,7 @@ static void set_images(const mw_dycore *h, StageParams &P, int buf) {
     D.base = nullptr;
     const bool decomposed = h->dir_active[d];
     if (d >= 2 && sim2d) continue;
+    if (bc_side(h, d)) continue;                           // a domain boundary: the halo holds boundary copies, not images
     int nxr = c.nx, nyr = c.ny;                            // the receiver's block
     if (!decomposed) { D.base = h->q[buf]; D.vstride = h->vstride; D.zstride = h->zstride; D.pitch = h->pitch; }
     else if (h->peer_halo) {
@@ -229,7 +250,8 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   MW_REQUIRE(cfg->ny_glob == 1 || cfg->ny >= HALO, "ny = %d too small for a 3-D run", cfg->ny);
   MW_REQUIRE(cfg->num_tracers >= 0 && cfg->num_tracers <= MW_MAX_TRACERS, "num_tracers = %d out of range", cfg->num_tracers);
   MW_REQUIRE(cfg->num_tracers <= 4, "num_tracers = %d: stage kernel is instantiated for 0..4 tracers", cfg->num_tracers);
-  MW_REQUIRE(cfg->bc_x == MW_BC_PERIODIC && cfg->bc_y == MW_BC_PERIODIC, "only periodic bc_x/bc_y are implemented");
+  for (int bc : {cfg->bc_x, cfg->bc_y})
+    MW_REQUIRE(bc == MW_BC_PERIODIC || bc == MW_BC_OPEN || bc == MW_BC_WALL, "bc_x / bc_y must be periodic, open or wall");
   MW_REQUIRE(cfg->bc_z == MW_BC_WALL || cfg->bc_z == MW_BC_OPEN, "bc_z must be wall or open");
   MW_REQUIRE(cfg->C0 > 0 && cfg->gamma_d > 1, "C0/gamma_d not set (call mw_config_defaults)");
   mw_dycore *h = new mw_dycore();
@@ -242,6 +264,8 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   h->qbytes = (size_t) h->N * h->vstride * sizeof(double);
   const char *e = getenv("MW_NO_TMA");
   h->use_tma = (e && atoi(e) != 0) ? 0 : 1;
+  e = getenv("MW_BC_BOTH_FACES");
+  h->bc_both_faces = e && atoi(e) != 0;
   const int T = cfg->num_tracers > 0 ? cfg->num_tracers : 1;
   const size_t nzl = cfg->nz, nyl = cfg->ny, nxl = cfg->nx;
   cudaError_t ce = cudaSuccess;
@@ -348,6 +372,14 @@ extern "C" int mw_dycore_update_options(mw_dycore *h, int enable_gravity, double
   return MW_OK;
 }
 
+extern "C" int mw_dycore_update_lateral_bc(mw_dycore *h, int bc_x, int bc_y) {
+  MW_REQUIRE(h, "mw_dycore_update_lateral_bc: null handle");
+  for (int bc : {bc_x, bc_y})
+    MW_REQUIRE(bc == MW_BC_PERIODIC || bc == MW_BC_OPEN || bc == MW_BC_WALL, "bc_x / bc_y must be periodic, open or wall");
+  h->cfg.bc_x = bc_x; h->cfg.bc_y = bc_y;
+  return MW_OK;
+}
+
 extern "C" double mw_dycore_compute_time_step(const mw_dycore *h) {      // DYC:70-77
   if (!h) return 0.0;
   const double maxwave = 350 + 80, cfl = 0.6;
@@ -446,13 +478,14 @@ static int exchange_halos(mw_dycore *h, double *q, cudaStream_t st) {
   MW_CUDA_OK(cudaGetLastError());
   int rc = exchange(h, h->hsend, h->hrecv, h->hcount, st);
   if (rc != MW_OK) return rc;
+  // a domain boundary's halo keeps its boundary copies: what the periodic neighbour sent is dropped
   if (h->dir_active[0]) {
-    H.buf[0] = h->hrecv[0]; H.buf[1] = h->hrecv[1];
+    H.buf[0] = bc_side(h, 0) ? nullptr : h->hrecv[0]; H.buf[1] = bc_side(h, 1) ? nullptr : h->hrecv[1];
     k_halo_x<false><<<dim3((unsigned) ((h->hcount[0] + 255) / 256), 2), 256, 0, st>>>(H);
     h->launches++;
   }
   if (h->dir_active[2]) {
-    H.buf[0] = h->hrecv[2]; H.buf[1] = h->hrecv[3];
+    H.buf[0] = bc_side(h, 2) ? nullptr : h->hrecv[2]; H.buf[1] = bc_side(h, 3) ? nullptr : h->hrecv[3];
     k_halo_y<false><<<dim3((unsigned) ((h->hcount[2] + 255) / 256), 2), 256, 0, st>>>(H);
     h->launches++;
   }
@@ -534,13 +567,20 @@ template <int NT> struct StageKernel {
   using C = CellCfg<NT>;
   static constexpr int TX = TILE_X;
   static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P) {
-    if (h->use_tma) k_stage_cell<NT, true><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P);
-    else k_stage_cell<NT, false><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P);
+    if (P.bc_any) {                                        // open / wall lateral boundaries: the instantiation that knows them
+      if (h->use_tma) k_stage_cell<NT, true, true><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P);
+      else k_stage_cell<NT, false, true><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P);
+    } else {
+      if (h->use_tma) k_stage_cell<NT, true, false><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P);
+      else k_stage_cell<NT, false, false><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P);
+    }
   }
   static cudaError_t attr() {
-    cudaError_t e = cudaFuncSetAttribute(k_stage_cell<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_stage_cell<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_stage_cell<NT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stage_cell<NT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stage_cell<NT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stage_cell<NT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+    return e;
   }
 };
 template <int NT>
@@ -928,7 +968,8 @@ extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields
   // decomposed runs: every rank must walk the same schedule, so the blocks must be equal
   const bool equal_blocks = c.nproc_x * c.nproc_y == 1 ||
                             (h->comm && c.nx_glob % c.nproc_x == 0 && c.ny_glob % c.nproc_y == 0 && c.nx == c.nx_glob / c.nproc_x && c.ny == c.ny_glob / c.nproc_y);
-  const bool pipelined = rows_per_slab >= 8 && equal_blocks && c.ny_glob > 1 && c.ny / rows_per_slab >= 4;
+  const bool periodic_xy = c.bc_x == MW_BC_PERIODIC && c.bc_y == MW_BC_PERIODIC;     // the slab schedule wraps around the seam
+  const bool pipelined = rows_per_slab >= 8 && equal_blocks && periodic_xy && c.ny_glob > 1 && c.ny / rows_per_slab >= 4;
   if (pipelined) {
     MW_CUDA_OK(cudaDeviceSynchronize());                  // the non-blocking streams do not order against earlier default-stream work
     int rc = 1;

@@ -15,6 +15,7 @@
 namespace mw {
 
 constexpr int HALO = 3;
+constexpr int MW_FBC_REF1 = 3;
 enum { idR = 0, idU = 1, idV = 2, idW = 3, idT = 4, NUM_STATE = 5 };
 
 struct StageParams {
@@ -48,6 +49,13 @@ struct StageParams {
   // factor array (peer memory).  base == nullptr where the local boundary is the global periodic seam (or the only rank
   // in that direction): factor 1 there, which is what the reference does with its two copies of a seam face (DYC:508-509)
   struct MultSrc { const double *base; long long st_t, st_k, st_i, off; } msrc[4];
+  // Open / wall lateral boundaries (DYC:782-825, :1040-1080), sides W, E, S, N; all zero in a periodic run (bc_any == 0).
+  // hbc[d] (MW_BC_OPEN / MW_BC_WALL): this rank's side d is a domain boundary -- its three halo columns / rows hold copies
+  // of the edge cell (normal velocity 0 at a wall), written by the kernel that produces the edge cell.  fbc[d]: what the
+  // boundary FACE sees -- MW_BC_OPEN: the outer state is the inner one; MW_BC_WALL: the same with the normal velocity zero
+  // on both sides; MW_FBC_REF1 (E, N only): the reference on ONE rank in that direction, whose `else if` (DYC:1051, :1072)
+  // leaves the face with the periodic neighbour's outer state, i.e. the low edge values of cell 0 of the row / column.
+  int hbc[4], fbc[4], bc_any;
   unsigned positive_mask;    // bit tr set <=> tracer tr must stay non-negative
   int use_tma;
   // which tiles a launch covers (halo exchange overlapped with interior compute): 0 = all (2-D grid), 1 = the interior
@@ -102,6 +110,12 @@ __device__ __forceinline__ int image_mask(const StageParams &P, int j, int i) {
   if (i >= P.nx - HALO && P.img[1].base) m |= 2;
   if (j < HALO && P.img[2].base) m |= 4;
   if (j >= P.ny - HALO && P.img[3].base) m |= 8;
+  if (P.bc_any) {                                        // boundary-condition copies into my own halo
+    if (i == 0 && P.hbc[0]) m |= 16;
+    if (i == P.nx - 1 && P.hbc[1]) m |= 32;
+    if (j == 0 && P.hbc[2]) m |= 64;
+    if (j == P.ny - 1 && P.hbc[3]) m |= 128;
+  }
   return m;
 }
 __device__ __forceinline__ void store_image(const StageParams &P, int d, int l, int k, int j, int i, double v) {
@@ -113,6 +127,13 @@ __device__ __forceinline__ void store_images(const StageParams &P, int mask, int
   if (mask & 2) store_image(P, 1, l, k, j, i, v);
   if (mask & 4) store_image(P, 2, l, k, j, i, v);
   if (mask & 8) store_image(P, 3, l, k, j, i, v);
+  if (mask & 0xf0) {                                     // DYC:782-825: the halo repeats the edge cell; a wall zeroes the normal velocity
+    double *c = P.qout + (long long) l * P.vstride + (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + HALO + i;
+    if (mask & 16)  { const double b = (l == idU && P.hbc[0] == MW_BC_WALL) ? 0.0 : v; c[-1] = b; c[-2] = b; c[-3] = b; }
+    if (mask & 32)  { const double b = (l == idU && P.hbc[1] == MW_BC_WALL) ? 0.0 : v; c[1] = b; c[2] = b; c[3] = b; }
+    if (mask & 64)  { const double b = (l == idV && P.hbc[2] == MW_BC_WALL) ? 0.0 : v; c[-P.pitch] = b; c[-2 * P.pitch] = b; c[-3 * P.pitch] = b; }
+    if (mask & 128) { const double b = (l == idV && P.hbc[3] == MW_BC_WALL) ? 0.0 : v; c[P.pitch] = b; c[2 * P.pitch] = b; c[3 * P.pitch] = b; }
+  }
 }
 __device__ __forceinline__ void store_with_images(const StageParams &P, int l, int k, int j, int i, double v) {
   P.qout[(long long) l * P.vstride + (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + HALO + i] = v;

@@ -75,11 +75,23 @@ __device__ __forceinline__ void face_flux(const double (&L)[N], const double (&R
   }
 }
 
+// Low edge values of n variables of one cell from global memory (stride st between the five stencil cells); out of line
+// and through local memory on purpose: only the MW_FBC_REF1 boundary faces call it (see phase 2 of the kernel)
+__device__ __noinline__ void ref1_low_edges(const double *q, long long st, long long vstride, int n, double *out) {
+  for (int v = 0; v < n; ++v, q += vstride) {
+    double lo, hi;
+    weno5_edges(q[-2 * st], q[-st], q[0], q[st], q[2 * st], lo, hi);
+    out[v] = lo;
+  }
+}
+
 // neighbour exchange along x inside a tile row (W = TX lanes)
 template <int W> __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1, W); }
 template <int W> __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1, W); }
 
-template <int NT, bool TMA>
+// LBC: instantiation with the open / wall lateral boundary code (launched only when StageParams::bc_any is set, so the
+// periodic path carries none of it)
+template <int NT, bool TMA, bool LBC>
 __global__ void __launch_bounds__(CellCfg<NT>::NTHR, 1)
 k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ CUtensorMap tmapI, const StageParams P) {
   using C = CellCfg<NT>;
@@ -331,6 +343,30 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     }
 
     // ================= phase 2: face fluxes =================
+    // Open / wall lateral boundaries (StageParams::fbc; never taken in a periodic run).  The reference on one rank leaves
+    // the east / north boundary face with the periodic neighbour's outer state (MW_FBC_REF1): the low edge values of cell 0
+    // of my row (x) / column (y), reconstructed here from the stage input in global memory -- cells -2 .. 2, the halo
+    // holds the boundary copies.
+    auto ref1_state = [&](bool ydir, double (&R)[N], double &pR) {
+      const int jj = min(gj, P.ny - 1), ii = min(gi, P.nx - 1);
+      const double *q = P.qin + (long long) k * P.zstride +
+                        (ydir ? (long long) HALO * P.pitch + (ii + HALO) : (long long) (jj + HALO) * P.pitch + HALO);
+      double tmp[N];                                         // in local memory (rare path); R itself stays in registers
+      ref1_low_edges(q, ydir ? P.pitch : 1, P.vstride, N, tmp);
+#pragma unroll
+      for (int v = 0; v < N; ++v) R[v] = tmp[v];
+      int b = 0;
+      pR = eos_pressure_series(R[idT], ihytc_k, pcell_k, P, b);
+      if (b) eos_repair(R[idT], hytc_k, pR);
+    };
+    // boundary face seen from inside: the outer state (O, pO) becomes the inner one (I, pI); a wall zeroes the normal velocity
+    auto bc_face = [&](int code, bool ydir, int idn, double (&I)[N], double pI, double (&O)[N], double &pO) {
+      if (code == MW_FBC_REF1) { ref1_state(ydir, O, pO); return; }
+#pragma unroll
+      for (int v = 0; v < N; ++v) O[v] = I[v];
+      pO = pI;
+      if (code == MW_BC_WALL) { I[idn] = 0.0; O[idn] = 0.0; }
+    };
     double tend[N];                                          // flux divergence, accumulated direction by direction
     double fox_keep[NT > 0 ? NT : 1];                        // outgoing part of the tracers' x face fluxes (FCT)
     {
@@ -343,14 +379,19 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
         for (int v = 0; v < N; ++v) L[v] = sm[C::OFF_RXH + v * TY + y];
         pL = sm[C::OFF_RXH + N * TY + y];
       }
+      if (LBC && P.bc_any) {
+        if (P.fbc[0] && gi == 0) bc_face(P.fbc[0], false, idU, lox, p_lox, L, pL);            // west boundary face
+        if (P.fbc[1] && gi == P.nx) bc_face(P.fbc[1], false, idU, L, pL, lox, p_lox);         // east one, ragged last tile
+      }
       face_flux<N, idU, false>(L, lox, pL, p_lox, hyc_k, hytc_k, f_lo);
 #pragma unroll
       for (int v = 0; v < N; ++v) f_hi[v] = shfl_dn1<TX>(f_lo[v]);
       if (x == TX - 1) {
-        double R[N];
+        double R[N], Lh[N], pR = sm[C::OFF_RXL + N * TY + y];
 #pragma unroll
-        for (int v = 0; v < N; ++v) R[v] = sm[C::OFF_RXL + v * TY + y];
-        face_flux<N, idU, false>(hix, R, p_hix, sm[C::OFF_RXL + N * TY + y], hyc_k, hytc_k, f_hi);
+        for (int v = 0; v < N; ++v) { R[v] = sm[C::OFF_RXL + v * TY + y]; Lh[v] = hix[v]; }
+        if (LBC && P.bc_any && P.fbc[1] && gi == P.nx - 1) bc_face(P.fbc[1], false, idU, Lh, p_hix, R, pR);   // east boundary face
+        face_flux<N, idU, false>(Lh, R, p_hix, pR, hyc_k, hytc_k, f_hi);
       }
       if (NT > 0 && gj < P.ny) {                             // tracer face fluxes for the FCT finish
         const long long gx = ((long long) k * P.ny + gj) * (P.nx + 1) + gi;
@@ -372,15 +413,20 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
 #pragma unroll
       for (int v = 0; v < N; ++v) L[v] = HY[(v * (TY + 1) + y) * TX + x];
       pL = HY[(N * (TY + 1) + y) * TX + x];
+      if (LBC && P.bc_any) {
+        if (P.fbc[2] && gj == 0) bc_face(P.fbc[2], true, idV, loy, p_loy, L, pL);             // south boundary face
+        if (P.fbc[3] && gj == P.ny) bc_face(P.fbc[3], true, idV, L, pL, loy, p_loy);          // north one, ragged last tile row
+      }
       face_flux<N, idV, false>(L, loy, pL, p_loy, hyc_k, hytc_k, fy_lo);
 #pragma unroll
       for (int v = 0; v < N; ++v) FY[(v * (TY + 1) + y) * TX + x] = fy_lo[v];
       double f_top[N];
       if (y == TY - 1) {
-        double R[N];
+        double R[N], Lh[N], pR = sm[C::OFF_RYL + N * TX + x];
 #pragma unroll
-        for (int v = 0; v < N; ++v) R[v] = sm[C::OFF_RYL + v * TX + x];
-        face_flux<N, idV, false>(hiy, R, p_hiy, sm[C::OFF_RYL + N * TX + x], hyc_k, hytc_k, f_top);
+        for (int v = 0; v < N; ++v) { R[v] = sm[C::OFF_RYL + v * TX + x]; Lh[v] = hiy[v]; }
+        if (LBC && P.bc_any && P.fbc[3] && gj == P.ny - 1) bc_face(P.fbc[3], true, idV, Lh, p_hiy, R, pR);    // north boundary face
+        face_flux<N, idV, false>(Lh, R, p_hiy, pR, hyc_k, hytc_k, f_top);
 #pragma unroll
         for (int v = 0; v < N; ++v) FY[(v * (TY + 1) + TY) * TX + x] = f_top[v];
       }

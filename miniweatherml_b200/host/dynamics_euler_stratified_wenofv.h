@@ -52,6 +52,8 @@ class Dynamics_Euler_Stratified_WenoFV {
                                        coupler.get_option<real>("latitude", 0.), coupler.get_option<real>("earthrot"),
                                        coupler.get_option<real>("C0"), coupler.get_option<real>("gamma_d"),
                                        coupler.get_option<int>("bc_z")), "mw_dycore_update_options");
+    mw::check(mw_dycore_update_lateral_bc(handle, coupler.get_option<int>("bc_x"), coupler.get_option<int>("bc_y")),
+              "mw_dycore_update_lateral_bc");
     if (coupler.get_option<bool>("use_immersed_boundaries", false) != (cfg.use_immersed_boundaries != 0)) {
       update_immersed(coupler);
       cfg.use_immersed_boundaries = coupler.get_option<bool>("use_immersed_boundaries", false) ? 1 : 0;

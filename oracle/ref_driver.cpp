@@ -83,7 +83,8 @@ static void usage() {
     "               [perturb=1] [in=state.bin] [out=state.bin] [out0=initial_state.bin] [bg=background.bin]\n"
     "               [precl=precl.bin] [time=0|1 print seconds per step] [warmup=0 untimed steps first]\n"
     "               [enable_gravity=1] [hsponge=0 (simple_city: Horizontal_Sponge init(10,1) + apply(x1,x2) before the dycore)]\n"
-    "               [sponge_ts=60] [imm=immersed_proportion.bin] [init_data=supercell|thermal|building|city]\n");
+    "               [sponge_ts=60] [imm=immersed_proportion.bin] [init_data=supercell|thermal|building|city]\n"
+    "               [bc_x=0|1|2] [bc_y=...] [bc_z=...]  (0 periodic, 1 open, 2 wall; DYC:46-48)\n");
 }
 
 static int mode_run(std::map<std::string,std::string> &kv) {
@@ -122,6 +123,8 @@ static int mode_run(std::map<std::string,std::string> &kv) {
     if (do_micro) { fprintf(stderr,"micro=1 needs tracers=kessler\n"); return 2; }
   }
   dycore.init( coupler );
+  // boundary conditions other than the ones init() sets (DYC:1332-1334): the dycore reads these options every step
+  for (const char *b : {"bc_x","bc_y","bc_z"}) if (kv.count(b)) coupler.set_option<int>( b , (int) geti(b,0) );
   if (do_hsponge) horiz_sponge.init( coupler , 10 , 1. );      // experiments/simple_city/driver.cpp:60
   column_nudger.set_column( coupler );
   if (do_perturb) modules::perturb_temperature( coupler );

@@ -24,7 +24,8 @@ class Params(C.Structure):
                 ("R_v", C.c_double), ("cp_d", C.c_double), ("p0", C.c_double), ("fcor", C.c_double),
                 ("sim2d", C.c_int), ("enable_gravity", C.c_int), ("use_immersed", C.c_int), ("bc_z", C.c_int),
                 ("idWV", C.c_int),
-                ("tracer_positive", C.c_int * MAX_TRACERS), ("tracer_adds_mass", C.c_int * MAX_TRACERS)]
+                ("tracer_positive", C.c_int * MAX_TRACERS), ("tracer_adds_mass", C.c_int * MAX_TRACERS),
+                ("bc_x", C.c_int), ("bc_y", C.c_int), ("ref_single_rank", C.c_int)]
 
 
 # Physical constants exactly as the reference derives them (KES:31-40 take precedence, DYC:1227-1247)
@@ -36,7 +37,7 @@ C0 = (R_D * P0 ** (-KAPPA)) ** GAMMA
 
 
 def make_params(nx, ny, nz, xlen, ylen, zlen, num_tracers, use_immersed=False, bc_z=2, fcor=0.0,
-                enable_gravity=True, idWV=0, positive=None, adds_mass=None):
+                enable_gravity=True, idWV=0, positive=None, adds_mass=None, bc_x=0, bc_y=0, ref_single_rank=False):
     p = Params()
     p.nx, p.ny, p.nz, p.num_tracers = nx, ny, nz, num_tracers
     p.dx, p.dy, p.dz = xlen / nx, ylen / ny, zlen / nz
@@ -45,6 +46,8 @@ def make_params(nx, ny, nz, xlen, ylen, zlen, num_tracers, use_immersed=False, b
     p.enable_gravity = 1 if enable_gravity else 0
     p.use_immersed = 1 if use_immersed else 0
     p.bc_z = bc_z
+    # ref_single_rank: True / False (both directions) or a bit mask (1: x, 2: y) of the directions held by ONE rank
+    p.bc_x, p.bc_y, p.ref_single_rank = bc_x, bc_y, (3 if ref_single_rank is True else int(ref_single_rank))
     p.idWV = idWV
     for t in range(num_tracers):
         p.tracer_positive[t] = 1 if positive is None else int(positive[t])

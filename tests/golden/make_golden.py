@@ -125,8 +125,27 @@ def ensemble_fixtures(tmp):
                         imm=imm[..., 0].copy(), dt=r[-1]["dt"], steps=3, **g)
 
 
+def lateral_bc_fixtures(tmp):
+    """Open / wall lateral boundaries (DYC:782-825, :1040-1080) and periodic z (DYC:752-763, :1008-1019).  No shipped case
+    sets them (DYC:1332-1334), so the driver overrides the options after dycore.init(); the dycore reads them every step.
+    One rank: the reference then leaves the east / north boundary FACE periodic (`else if`, DYC:1051, :1072) -- the
+    fixtures hold exactly that."""
+    g = dict(nx=24, ny=20, nz=16, xlen=24e3, ylen=20e3, zlen=16e3)
+    for name, bc in [("open_wall", dict(bc_x=1, bc_y=2)), ("wall_open", dict(bc_x=2, bc_y=1)), ("zperiodic", dict(bc_z=0))]:
+        s0, s1, bg, meta = run_states(tmp, tracers="vapor", steps=4, **g, **bc)
+        np.savez_compressed(HERE + "/box3d_bc_%s_dycore4.npz" % name, s0=s0, s1=s1, bg=bg, dt=meta["dt"], steps=4,
+                            bc_x=bc.get("bc_x", 0), bc_y=bc.get("bc_y", 0), bc_z=bc.get("bc_z", 2), **g)
+    g = dict(nx=40, ny=1, nz=20, xlen=4e4, ylen=4e4, zlen=2e4)
+    s0, s1, bg, meta = run_states(tmp, tracers="kessler", steps=5, bc_x=2, **g)
+    np.savez_compressed(HERE + "/box2d_bc_wall_dycore5.npz", s0=s0, s1=s1, bg=bg, dt=meta["dt"], steps=5,
+                        bc_x=2, bc_y=0, bc_z=2, **g)
+
+
 def main():
     tmp = tempfile.mkdtemp()
+    if "--bc" in sys.argv:
+        lateral_bc_fixtures(tmp)
+        return
     if "--ensemble" in sys.argv:
         ensemble_fixtures(tmp)
         return

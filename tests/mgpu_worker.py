@@ -41,6 +41,8 @@ def main():
     nxg, nyg, T, steps = [int(a) for a in sys.argv[1:5]]
     physics = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     host = int(sys.argv[6]) if len(sys.argv) > 6 else 0          # also run the slab-pipelined host-buffer step on every rank
+    bc_x = int(sys.argv[7]) if len(sys.argv) > 7 else 0          # lateral boundary conditions (0 periodic, 1 open, 2 wall)
+    bc_y = int(sys.argv[8]) if len(sys.argv) > 8 else 0
     torch.cuda.set_device(lrank)
     dev = torch.device("cuda", lrank)
     dist.init_process_group("nccl", device_id=dev)
@@ -56,7 +58,7 @@ def main():
     j_beg, ny = mwd.block_range(nyg, npy, py)
     xlen, ylen = nxg * 1000.0, nyg * 1000.0
     cfg = mw.make_config(nx, ny, nz, xlen, ylen, zlen, T, nx_glob=nxg, ny_glob=nyg, i_beg=i_beg, j_beg=j_beg,
-                         nproc_x=npx, nproc_y=npy, px=px, py=py)
+                         nproc_x=npx, nproc_y=npy, px=px, py=py, bc_x=bc_x, bc_y=bc_y)
     dy = mw.Dycore(cfg)
     dy.set_background(g["bg"])
     dy.attach_comm(comm)
@@ -103,7 +105,9 @@ def main():
             dist.recv(buf, src=r)
             out[:, :, jb:jb + nyy, ib:ib + nxx] = buf.cpu().numpy()
         ref = s0.copy()
-        p = O.make_params(nxg, nyg, nz, xlen, ylen, zlen, T)
+        # a direction held by ONE rank gets the reference's one-rank boundary faces (DYC:1051, :1072), the others both
+        p = O.make_params(nxg, nyg, nz, xlen, ylen, zlen, T, bc_x=bc_x, bc_y=bc_y,
+                          ref_single_rank=(1 if npx == 1 else 0) | (2 if npy == 1 else 0))
         if physics:
             col_ref = O.column_average([np.ascontiguousarray(ref[i]) for i in idx])
         for _ in range(steps):

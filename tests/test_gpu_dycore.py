@@ -129,6 +129,48 @@ def test_dycore_ragged_sizes_vs_oracle(golden, nx, ny, T):
         assert relmax(out[l], ref[l]) <= TOL, (l, relmax(out[l], ref[l]))
 
 
+@pytest.mark.parametrize("name", ["box3d_bc_open_wall_dycore4.npz", "box3d_bc_wall_open_dycore4.npz", "box2d_bc_wall_dycore5.npz"])
+def test_lateral_bc_vs_reference_golden(golden, name):
+    """Open / wall lateral boundaries against the compiled reference on one rank (DYC:782-825, :1040-1080), including its
+    one-rank treatment of the east / north boundary face (DYC:1051, :1072)."""
+    g = golden(name)
+    T = g["s0"].shape[0] - 5
+    out, _ = gpu_run(g, g["s0"], int(g["steps"]), float(g["dt"]), T, bc_x=int(g["bc_x"]), bc_y=int(g["bc_y"]))
+    for l in range(5 + T):
+        assert relmax(out[l], g["s1"][l]) <= TOL, (l, relmax(out[l], g["s1"][l]))
+
+
+@pytest.mark.parametrize("nx,ny,T,bc_x,bc_y,both", [(37, 19, 1, 2, 1, 1), (64, 16, 2, 1, 2, 1), (64, 16, 2, 2, 2, 0), (45, 11, 3, 1, 1, 0),
+                                                    (70, 1, 3, 2, 0, 1), (32, 8, 0, 2, 1, 0), (40, 24, 1, 0, 2, 1), (33, 40, 1, 1, 0, 0)])
+def test_lateral_bc_sizes_vs_oracle(golden, monkeypatch, nx, ny, T, bc_x, bc_y, both):
+    """Ragged and tile-aligned sizes (the boundary face is a ring face of the last tile or an interior face of a ragged
+    one), every combination of open / wall / periodic; both = 1: the two-or-more-ranks treatment of the east / north
+    face (MW_BC_BOTH_FACES) against the oracle's, both = 0: the reference's one-rank treatment"""
+    if both:
+        monkeypatch.setenv("MW_BC_BOTH_FACES", "1")
+    g = golden("box3d_vapor_dycore5.npz")
+    nz = int(g["nz"])
+    gg = dict(xlen=nx * 1000.0, ylen=max(ny, 1) * 1000.0, zlen=float(g["zlen"]), bg=g["bg"])
+    s0 = synthetic_state(g, nz, ny, nx, max(T, 1), seed=nx * 100 + ny)
+    dt = 0.6 * min(1000.0, float(g["zlen"]) / nz) / 430.0
+    if T == 0:
+        s0[5] = 0.0
+    p = O.make_params(nx, ny, nz, gg["xlen"], gg["ylen"], gg["zlen"], max(T, 1), bc_x=bc_x, bc_y=bc_y, ref_single_rank=not both)
+    ref = s0.copy()
+    O.dycore_step(p, g["bg"], ref, dt, steps=3)
+    out, _ = gpu_run(gg, s0[:5 + T], 3, dt, T, bc_x=bc_x, bc_y=bc_y)
+    for l in range(5 + T):
+        assert relmax(out[l], ref[l]) <= TOL, (l, relmax(out[l], ref[l]))
+
+
+def test_lateral_bc_plain_load_path_agrees(golden, monkeypatch):
+    g = golden("box3d_bc_wall_open_dycore4.npz")
+    a, _ = gpu_run(g, g["s0"], 2, float(g["dt"]), 1, bc_x=2, bc_y=1)
+    monkeypatch.setenv("MW_NO_TMA", "1")
+    b, _ = gpu_run(g, g["s0"], 2, float(g["dt"]), 1, bc_x=2, bc_y=1)
+    assert np.array_equal(a, b)
+
+
 def test_dycore_immersed_and_subcycling_vs_oracle(golden):
     """Immersed-boundary relaxation (DYC:534-550) and dt_phys > dt_dyn sub-cycling (DYC:104-110).  A smooth state with
     non-zero v and w is used: with v = w = 0 exactly the upwind switch `m_L + m_R > 0` is decided by rounding noise and

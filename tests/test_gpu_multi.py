@@ -33,6 +33,17 @@ def test_decomposition_independence(nproc, nxg, nyg, T, physics):
     assert r["ok"], r
 
 
+@pytest.mark.parametrize("nproc,nxg,nyg,T,bc_x,bc_y", [(2, 40, 36, 1, 2, 1), (2, 36, 40, 3, 1, 2), (4, 44, 40, 2, 2, 2), (4, 64, 48, 1, 1, 0),
+                                                       (8, 64, 48, 1, 1, 2)])
+def test_lateral_boundaries_on_decomposed_grids(nproc, nxg, nyg, T, bc_x, bc_y):
+    """Open / wall lateral boundaries (DYC:782-825, :1040-1080) with rank boundaries inside the domain: the boundary ranks
+    keep their boundary copies (nothing from the periodic neighbour), interior rank boundaries exchange as usual"""
+    if _ngpu() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    r = _run(nproc, [nxg, nyg, T, 3, 0, 0, bc_x, bc_y], 29800 + nproc + T)
+    assert r["ok"], r
+
+
 @pytest.mark.parametrize("nproc,nxg,nyg,T", [(2, 48, 160, 1), (2, 48, 160, 2), (4, 64, 160, 3)])
 def test_pipelined_host_step_on_a_decomposed_grid(nproc, nxg, nyg, T):
     """mw_dycore_time_step_host with rank neighbours (y only at 2 ranks, x and y at 4): slab-pipelined with the halo and

@@ -1,6 +1,7 @@
 """CPU tests: the plain-C restatement (oracle/mw_oracle.c) against the committed golden fixtures that were
 produced by the compiled reference (tests/golden/make_golden.py).  This is what pins the oracle."""
 import numpy as np
+import pytest
 import _oracle as O
 
 
@@ -194,3 +195,33 @@ def test_shipped_surrogate_weights_kat(golden):
     assert g["w"].shape == (104,) and g["scl_in"].shape == (5, 2) and g["scl_out"].shape == (4, 2)
     assert np.array_equal(O.mlp_forward(g["w"], g["x"]), g["y"])              # compiled ponni layers, same roundings
     assert np.array_equal(O.mlp_dense2(g["w"], g["x"], 10, 4), g["y"])
+
+
+@pytest.mark.parametrize("name", ["box3d_bc_open_wall_dycore4.npz", "box3d_bc_wall_open_dycore4.npz",
+                                  "box3d_bc_zperiodic_dycore4.npz", "box2d_bc_wall_dycore5.npz"])
+def test_dycore_lateral_boundary_conditions(golden, name):
+    """Open / wall bc_x, bc_y (DYC:782-825, :1040-1080) and periodic bc_z (DYC:752-763, :1008-1019): the reference run on
+    one rank (where its `else if` at DYC:1051 / :1072 leaves the east / north boundary face periodic) is what the oracle's
+    ref_single_rank mode restates; the two-or-more-ranks mode differs from it next to those faces only."""
+    g = golden(name)
+    T = g["s0"].shape[0] - 5
+    kw = dict(bc_x=int(g["bc_x"]), bc_y=int(g["bc_y"]), bc_z=int(g["bc_z"]))
+    out = {}
+    for single in (True, False):
+        p = O.make_params(int(g["nx"]), int(g["ny"]), int(g["nz"]), float(g["xlen"]), float(g["ylen"]), float(g["zlen"]), T,
+                          ref_single_rank=single, **kw)
+        f = np.ascontiguousarray(g["s0"].copy())
+        O.dycore_step(p, g["bg"], f, float(g["dt"]), steps=int(g["steps"]))
+        out[single] = f
+    for l in range(5 + T):
+        den = max(np.abs(g["s1"][l]).max(), 1e-300)
+        assert np.abs(out[True][l] - g["s1"][l]).max() / den <= 1e-13, l
+    if kw["bc_x"] or kw["bc_y"]:
+        # the other mode changes the east / north faces only: after `steps` steps the difference has travelled at most
+        # steps * 3 stages * 3 cells (stencil reach) from them
+        reach = int(g["steps"]) * 9 + 1
+        d = np.abs(out[True] - out[False])
+        assert d.max() > 0
+        nx, ny = int(g["nx"]), int(g["ny"])
+        far = d[:, :, : max(ny - reach, 0) if kw["bc_y"] else ny, : max(nx - reach, 0) if kw["bc_x"] else nx]
+        assert far.size == 0 or far.max() == 0.0
