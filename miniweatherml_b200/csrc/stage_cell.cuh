@@ -85,6 +85,13 @@ __device__ __noinline__ void ref1_low_edges(const double *q, long long st, long 
   }
 }
 
+// The images of an edge cell's n state variables (periodic wrap, a neighbour rank's halo, boundary copies).  Out of line:
+// few threads have any, and inlined the address arithmetic of four destinations per variable adds 15 % to the kernel's
+// instruction footprint (measured: 5.14 -> 5.30 ms per launch at config 2 through instruction-cache misses).
+__device__ __noinline__ void store_images_cold(const StageParams *P, int mask, int k, int j, int i, const double *v, int n) {
+  for (int l = 0; l < n; ++l) store_images(*P, mask, l, k, j, i, v[l]);
+}
+
 // neighbour exchange along x inside a tile row (W = TX lanes)
 template <int W> __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1, W); }
 template <int W> __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1, W); }
@@ -93,7 +100,8 @@ template <int W> __device__ __forceinline__ double shfl_dn1(double v) { return _
 // periodic path carries none of it)
 template <int NT, bool TMA, bool LBC>
 __global__ void __launch_bounds__(CellCfg<NT>::NTHR, 1)
-k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ CUtensorMap tmapI, const StageParams P) {
+k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ CUtensorMap tmapI,
+             const __grid_constant__ StageParams P) {
   using C = CellCfg<NT>;
   constexpr int N = C::N, TX = C::TX, TY = C::TY, PX = C::PX, PLANE = C::PLANE, NHS = C::NHS, NIS = C::NIS, IPL = C::IPL;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -463,6 +471,9 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
       const double rhoP_new = (P.rk_a * (rho0 - hyc_k) + P.rk_b * rhoP_k) + P.rk_cdt * tR;
       const double r_new = fast_rcp(rhoP_new + hyc_k);
       double *qo = P.qout + hcell;
+      double outv[NUM_STATE];                                // the new state of my cell, for its images
+#pragma unroll
+      for (int l = 0; l < NUM_STATE; ++l) outv[l] = 0.0;
 #pragma unroll
       for (int l = 0; l < N; ++l, qo += P.vstride) {
         if (in_dom) {
@@ -486,7 +497,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
               out = (l == idT) ? qn : qn * r_new;
             }
             qo[0] = out;
-            if (img) store_images(P, img, l, k, gj, gi, out);
+            outv[l] = out;
           } else {
             // tracer: leave the RK base value in qout and the FCT factor in mult for k_tracer_update
             const int tr = l - NUM_STATE;
@@ -504,6 +515,12 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
             qo[0] = P.rk_a * q0c + P.rk_b * qc;
           }
         }
+      }
+      if (img) {
+        double tmp[NUM_STATE];
+#pragma unroll
+        for (int l = 0; l < NUM_STATE; ++l) tmp[l] = outv[l];
+        store_images_cold(&P, img, k, gj, gi, tmp, NUM_STATE);
       }
     }
 #pragma unroll
