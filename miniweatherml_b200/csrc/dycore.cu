@@ -204,6 +204,8 @@ static void set_images(const mw_dycore *h, StageParams &P, int buf) {
   for (int d = 0; d < 4; ++d) {
     StageParams::ImgDst &D = P.img[d];
     D.base = nullptr;
+    P.idelta[d] = 0;
+    if (d == 0) P.ifast = 0;
     const bool decomposed = h->dir_active[d];
     if (d >= 2 && sim2d) continue;
     if (bc_side(h, d)) continue;                           // a domain boundary: the halo holds boundary copies, not images
@@ -219,6 +221,10 @@ static void set_images(const mw_dycore *h, StageParams &P, int buf) {
     if (d == 1) D.col0 = HALO - c.nx;                      // i in [nx-3, nx)   -> its west halo columns i - nx + 3
     if (d == 2) D.row0 = nyr + HALO;
     if (d == 3) D.row0 = HALO - c.ny;
+    if (D.vstride == h->vstride && D.zstride == h->zstride && D.pitch == h->pitch) {
+      P.idelta[d] = (D.base - h->q[buf]) + (long long) (D.row0 - HALO) * D.pitch + (D.col0 - HALO);
+      P.ifast |= 1 << d;
+    }
   }
 }
 

@@ -44,6 +44,11 @@ struct StageParams {
   // base == nullptr: nobody to write to (NCCL exchange mode fills that halo).  Image of cell (l, k, j, i):
   //   base + l*vstride + k*zstride + (row0 + j)*pitch + (col0 + i)
   struct ImgDst { double *base; long long vstride, zstride; int pitch, row0, col0; } img[4];
+  // Fast form: where the destination has my strides (always in my own buffer, and in a neighbour's when the blocks are
+  // equal) the image of a cell sits at a fixed distance idelta[d] (doubles) from the cell itself -- one store with a
+  // uniform offset instead of the address arithmetic above.  Bit d of ifast: destination d takes the fast form.
+  long long idelta[4];
+  int ifast;
   // FCT factors of the neighbouring rank's boundary cells, W / E / S / N: value(tr, k, idx) = base[tr*st_t + k*st_k +
   // idx*st_i + off], idx = j for W / E and i for S / N.  Either a packed strip received over NCCL or the neighbour's own
   // factor array (peer memory).  base == nullptr where the local boundary is the global periodic seam (or the only rank
@@ -135,10 +140,27 @@ __device__ __forceinline__ void store_images(const StageParams &P, int mask, int
     if (mask & 128) { const double b = (l == idV && P.hbc[3] == MW_BC_WALL) ? 0.0 : v; c[P.pitch] = b; c[2 * P.pitch] = b; c[3 * P.pitch] = b; }
   }
 }
+// the images in fast form: cell = address of the cell itself in qout
+__device__ __forceinline__ void store_images_fast(const StageParams &P, int mask, double *cell, double v) {
+  if (mask & 1) cell[P.idelta[0]] = v;
+  if (mask & 2) cell[P.idelta[1]] = v;
+  if (mask & 4) cell[P.idelta[2]] = v;
+  if (mask & 8) cell[P.idelta[3]] = v;
+}
+// The images that have no fast form (a neighbour with other strides, boundary copies), out of line: few threads have
+// any, and inlined their address arithmetic triples the instruction footprint of the conversion kernels.  P must live
+// in parameter space (__grid_constant__), not in a thread-local copy.
+__device__ __noinline__ void store_images_slow(const StageParams *P, int mask, int l, int k, int j, int i, double v) {
+  store_images(*P, mask, l, k, j, i, v);
+}
 __device__ __forceinline__ void store_with_images(const StageParams &P, int l, int k, int j, int i, double v) {
-  P.qout[(long long) l * P.vstride + (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + HALO + i] = v;
+  double *cell = P.qout + ((long long) l * P.vstride + (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + HALO + i);
+  *cell = v;
   const int m = image_mask(P, j, i);
-  if (m) store_images(P, m, l, k, j, i, v);
+  if (m) {
+    if (m & P.ifast) store_images_fast(P, m & P.ifast, cell, v);
+    if (m & ~P.ifast) store_images_slow(&P, m & ~P.ifast, l, k, j, i, v);
+  }
 }
 __device__ __forceinline__ double neighbour_mult(const StageParams &P, int d, int tr, int k, int idx) {
   const StageParams::MultSrc &M = P.msrc[d];
@@ -252,9 +274,9 @@ __device__ __forceinline__ void tracer_finish_cell(const StageParams &P, const C
 }
 
 template <int NT>
-__global__ void __launch_bounds__(256) k_tracer_update(const StageParams P) { tracer_finish_cell<NT, false>(P, nullptr); }
+__global__ void __launch_bounds__(256) k_tracer_update(const __grid_constant__ StageParams P) { tracer_finish_cell<NT, false>(P, nullptr); }
 template <int NT>
-__global__ void __launch_bounds__(256) k_tracer_update_d2c(const StageParams P, const __grid_constant__ ConvertParams Q) {
+__global__ void __launch_bounds__(256) k_tracer_update_d2c(const __grid_constant__ StageParams P, const __grid_constant__ ConvertParams Q) {
   tracer_finish_cell<NT, true>(P, &Q);
 }
 
@@ -262,7 +284,7 @@ __global__ void __launch_bounds__(256) k_tracer_update_d2c(const StageParams P, 
 // Coupler <-> dycore form (DYC:1955-2015 and DYC:1891-1951)
 // --------------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(256) k_coupler_to_dyn(const ConvertParams Q) {
+__global__ void __launch_bounds__(256) k_coupler_to_dyn(const __grid_constant__ ConvertParams Q) {
   const StageParams &P = Q.S;
   const long long t0 = (long long) blockIdx.x * blockDim.x + threadIdx.x, tstride = (long long) gridDim.x * blockDim.x;
   int i[CONV_CPT], j[CONV_CPT], k[CONV_CPT];

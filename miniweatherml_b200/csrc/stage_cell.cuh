@@ -186,7 +186,10 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
   // ---- running offsets ----------------------------------------------------------------------------------------------
   long long hcell = (long long) (min(gj, P.ny - 1) + HALO) * P.pitch + (min(gi, P.nx - 1) + HALO);   // haloed arrays
   long long gcell = (long long) min(gj, P.ny - 1) * P.nx + min(gi, P.nx - 1);                         // plain arrays
-  const int img = in_dom ? image_mask(P, gj, gi) : 0;       // images of my cell: periodic wrap or a neighbour rank's halo (peer memory)
+  // images of my cell (periodic wrap, a neighbour rank's halo in peer memory, boundary copies): the ones at a fixed
+  // distance from the cell are stored inline, the others (unequal blocks, boundary conditions) out of line
+  const int img_all = in_dom ? image_mask(P, gj, gi) : 0;
+  const int imgf = img_all & P.ifast, img = img_all & ~P.ifast;
   const bool have_q0 = P.rk_a != 0.0;
   const int hoff = (y + HALO) * PX + (x + HALO);             // my cell in a haloed plane slot
   double *HY = sm + C::OFF_HY, *FY = sm + C::OFF_FY;
@@ -497,6 +500,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
               out = (l == idT) ? qn : qn * r_new;
             }
             qo[0] = out;
+            if (imgf) store_images_fast(P, imgf, qo, out);
             outv[l] = out;
           } else {
             // tracer: leave the RK base value in qout and the FCT factor in mult for k_tracer_update

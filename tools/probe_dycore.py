@@ -1,7 +1,7 @@
 """Quick device-time probe of the dycore step on a synthetic supercell-shaped grid (not the bench)."""
 import sys, os, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.environ.get("MW_PKG_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # MW_PKG_ROOT: A/B against another build
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch
 import miniweatherml_b200 as mw
