@@ -260,6 +260,8 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
     MW_REQUIRE(bc == MW_BC_PERIODIC || bc == MW_BC_OPEN || bc == MW_BC_WALL, "bc_x / bc_y must be periodic, open or wall");
   MW_REQUIRE(cfg->bc_z == MW_BC_WALL || cfg->bc_z == MW_BC_OPEN, "bc_z must be wall or open");
   MW_REQUIRE(cfg->C0 > 0 && cfg->gamma_d > 1, "C0/gamma_d not set (call mw_config_defaults)");
+  MW_REQUIRE((double) (cfg->nz + 1) * (cfg->ny + 1) * (cfg->nx + 1) < 2147483647.0, "block of %d x %d x %d cells: the face arrays are indexed with 32 bits",
+             cfg->nx, cfg->ny, cfg->nz);
   mw_dycore *h = new mw_dycore();
   h->cfg = *cfg;
   h->N = NUM_STATE + cfg->num_tracers;
@@ -572,7 +574,12 @@ static int exchange_halos_async(mw_dycore *h, double *q, cudaStream_t st) {
 template <int NT> struct StageKernel {
   using C = CellCfg<NT>;
   static constexpr int TX = TILE_X;
-  static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P) {
+  static void launch(dim3 g, cudaStream_t st, const mw_dycore *h, int b, const StageParams &P0) {
+    StageParams P = P0;
+    {                                                      // DYC:536-542, once per launch instead of per cell and level
+      const double dtI = P.dt_stage, tau = 1.e3 * P.dt_stage;
+      P.imm_c = -fmin(1.0, dtI / tau) / dtI;
+    }
     if (P.bc_any) {                                        // open / wall lateral boundaries: the instantiation that knows them
       if (h->use_tma) k_stage_cell<NT, true, true><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P);
       else k_stage_cell<NT, false, true><<<g, C::NTHR, C::SMEM, st>>>(h->tmap[b], h->tmapI[b], P);

@@ -36,6 +36,7 @@ struct StageParams {
   double C0, gamma, grav, fcor;
   double rk_a, rk_b, rk_cdt; // q_new = rk_a*q0 + rk_b*q + rk_cdt*L(q)
   double dt_stage;           // the dt handed to compute_tendencies (FCT and immersed time scale), DYC:119,136,157
+  double imm_c;              // immersed tendency = imm_c * q, imm_c = -min(1, dt/tau)/dt with tau = 1e3 dt (DYC:536-542); set at launch
   int sim2d, bc_z, enable_gravity, use_immersed;
   // Where the images of my edge cells go: img[0] takes the cells with i < 3 (into the east halo of the west neighbour),
   // img[1] those with i >= nx-3 (west halo of the east neighbour), img[2] / img[3] the same for j (south / north).  The

@@ -405,10 +405,11 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
         face_flux<N, idU, false>(Lh, R, p_hix, pR, hyc_k, hytc_k, f_hi);
       }
       if (NT > 0 && gj < P.ny) {                             // tracer face fluxes for the FCT finish
-        const long long gx = ((long long) k * P.ny + gj) * (P.nx + 1) + gi;
+        const int gx = (k * P.ny + gj) * (P.nx + 1) + gi;    // face index inside one tracer's array: < 2^31 (checked at create)
+        const long long fxt = (long long) nz * P.ny * (P.nx + 1);
 #pragma unroll
         for (int l = NUM_STATE; l < N; ++l) {
-          double *fxg = P.flux_x + (long long) (l - NUM_STATE) * nz * ((long long) P.ny * (P.nx + 1)) + gx;
+          double *fxg = P.flux_x + ((l - NUM_STATE) * fxt + gx);
           if (gi <= P.nx) fxg[0] = f_lo[l];
           if (x == TX - 1 && gi + 1 <= P.nx) fxg[1] = f_hi[l];
         }
@@ -442,10 +443,11 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
         for (int v = 0; v < N; ++v) FY[(v * (TY + 1) + TY) * TX + x] = f_top[v];
       }
       if (NT > 0 && gi < P.nx) {
-        const long long gy = ((long long) k * (P.ny + 1) + gj) * P.nx + gi;
+        const int gy = (k * (P.ny + 1) + gj) * P.nx + gi;
+        const long long fyt = (long long) nz * (P.ny + 1) * P.nx;
 #pragma unroll
         for (int l = NUM_STATE; l < N; ++l) {
-          double *fyg = P.flux_y + (long long) (l - NUM_STATE) * nz * ((long long) (P.ny + 1) * P.nx) + gy;
+          double *fyg = P.flux_y + ((l - NUM_STATE) * fyt + gy);
           if (gj <= P.ny) fyg[0] = fy_lo[l];
           if (y == TY - 1 && gj + 1 <= P.ny) fyg[P.nx] = f_top[l];
         }
@@ -464,8 +466,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
       const double rho_k = Ik[idR * IPL] + hyc_k;
       const double u_k = Ik[idU * IPL], v_k = Ik[idV * IPL];
       const double rho0 = q0v[idR] + hyc_k;
-      const double dtI = P.dt_stage, tau = 1.e3 * P.dt_stage;
-      const double imm_c = -fmin(1.0, dtI / tau) / dtI;      // immersed tendency = imm_c * q   (DYC:536-542)
+      const double imm_c = P.imm_c;                          // immersed tendency = imm_c * q   (DYC:536-542)
       double tR = tend[idR];
       if (!sim2d) tR -= (fy_hi[idR] - fy_lo[idR]) * P.rdy;
       tR -= (fz_hi[idR] - fz_lo[idR]) * P.rdz;
@@ -477,9 +478,10 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
       double outv[NUM_STATE];                                // the new state of my cell, for its images
 #pragma unroll
       for (int l = 0; l < NUM_STATE; ++l) outv[l] = 0.0;
+      // straight-line: out-of-domain threads of a ragged tile compute on the zero fill and only their stores are masked
 #pragma unroll
       for (int l = 0; l < N; ++l, qo += P.vstride) {
-        if (in_dom) {
+        {
           const double val_k = Ik[l * IPL];
           double t = tend[l];
           if (!sim2d) t -= (fy_hi[l] - fy_lo[l]) * P.rdy;
@@ -499,8 +501,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
               const double qn = (P.rk_a * q0c + P.rk_b * qc) + P.rk_cdt * t;
               out = (l == idT) ? qn : qn * r_new;
             }
-            qo[0] = out;
-            if (imgf) store_images_fast(P, imgf, qo, out);
+            if (in_dom) qo[0] = out;
             outv[l] = out;
           } else {
             // tracer: leave the RK base value in qout and the FCT factor in mult for k_tracer_update
@@ -513,12 +514,20 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
               const double foy = sim2d ? 0.0 : (fmax(fy_hi[l], 0.0) - fmin(fy_lo[l], 0.0)) * P.rdy;
               const double foz = (fmax(fz_hi[l], 0.0) - fmin(fz_lo[l], 0.0)) * P.rdz;
               const double mass_out = (fox + foy + foz) * P.dt_stage * vol;
-              if (mass_out > mass_available) m = mass_available / mass_out;
+              const bool limit = mass_out > mass_available;     // rare (a nearly emptied cell): keep the division out of the common path
+              if (__any_sync(0xffffffffu, limit)) { if (limit) m = mass_available / mass_out; }
             }
-            P.mult[(long long) tr * nz * plane_cells + gcell] = m;
-            qo[0] = P.rk_a * q0c + P.rk_b * qc;
+            if (in_dom) {
+              P.mult[(long long) tr * nz * plane_cells + gcell] = m;
+              qo[0] = P.rk_a * q0c + P.rk_b * qc;
+            }
           }
         }
+      }
+      if (imgf) {                                            // images at a fixed distance from the cell
+        double *qi = P.qout + hcell;
+#pragma unroll
+        for (int l = 0; l < NUM_STATE; ++l, qi += P.vstride) store_images_fast(P, imgf, qi, outv[l]);
       }
       if (img) {
         double tmp[NUM_STATE];
