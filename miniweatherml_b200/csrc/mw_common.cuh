@@ -142,6 +142,32 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {
     if (spin > (1 << 22)) __trap();
   }
 }
+// The same for a hot loop: the barrier by its shared-memory address (computed once by the caller) and one try_wait on the
+// fast path -- the data is almost always there (planes are requested levels ahead); the polling loop is out of line.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity) {
+  uint32_t done = 0;
+  for (int spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity), "r"(20000u)
+        : "memory");
+    if (spin > (1 << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_fast(uint32_t a, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(done)
+      : "r"(a), "r"(parity)
+      : "memory");
+  if (!done) mbar_wait_slow(a, parity);
+}
 // generic-proxy writes/reads of a smem buffer must be ordered before the async proxy (TMA) overwrites it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
