@@ -151,8 +151,12 @@ __device__ __forceinline__ void store_images_fast(const StageParams &P, int mask
 // The images that have no fast form (a neighbour with other strides, boundary copies), out of line: few threads have
 // any, and inlined their address arithmetic triples the instruction footprint of the conversion kernels.  P must live
 // in parameter space (__grid_constant__), not in a thread-local copy.
-__device__ __noinline__ void store_images_slow(const StageParams *P, int mask, int l, int k, int j, int i, double v) {
+static __device__ __noinline__ void store_images_slow(const StageParams *P, int mask, int l, int k, int j, int i, double v) {
   store_images(*P, mask, l, k, j, i, v);
+}
+// the same for the first n variables of a cell at once (v in local memory): one call site per cell
+static __device__ __noinline__ void store_images_cold(const StageParams *P, int mask, int k, int j, int i, const double *v, int n) {
+  for (int l = 0; l < n; ++l) store_images(*P, mask, l, k, j, i, v[l]);
 }
 __device__ __forceinline__ void store_with_images(const StageParams &P, int l, int k, int j, int i, double v) {
   double *cell = P.qout + ((long long) l * P.vstride + (long long) k * P.zstride + (long long) (j + HALO) * P.pitch + HALO + i);
@@ -171,7 +175,7 @@ __device__ __forceinline__ double neighbour_mult(const StageParams &P, int d, in
 // p = C0 * rt^gamma  (DYC:401).  rt = bg + rtp with |rtp/bg| of a few percent in every shipped test case, so
 // p = p_bg * (1+e)^gamma is summed as a degree-11 binomial series (truncation < 1.3e-15 relative for |e| <= 0.1);
 // anything larger takes the exact pow() slow path, so no input can silently lose accuracy.
-__device__ __noinline__ double eos_pressure_slow(double rt, double C0, double gamma) { return C0 * pow(rt, gamma); }
+static __device__ __noinline__ double eos_pressure_slow(double rt, double C0, double gamma) { return C0 * pow(rt, gamma); }
 __device__ __forceinline__ double eos_pressure(double rtp, double bg, double inv_bg, double p_bg, const StageParams &P) {
   const double e = rtp * inv_bg;
   if (fabs(e) > 0.1) return eos_pressure_slow(bg + rtp, P.C0, P.gamma);
@@ -314,16 +318,34 @@ __global__ void __launch_bounds__(256) k_coupler_to_dyn(const __grid_constant__ 
 #pragma unroll
     for (int tr = 0; tr < NT; ++tr) if (tr == Q.idWV) rho_v = trv[u][tr];
     const double press = rho_d * Q.R_d * temp + rho_v * Q.R_v * temp;
+    // libm pow on purpose: the shared-logarithm power of fastmath.cuh (a few 1e-15 relative) was measured here -- 0.25 ms
+    // faster per step, but its rounding noise in p is ten times the reference's and shows up as 1e-8 relative in the
+    // weakest field (v in the city cases, |v| ~ 1e-3 m/s) after six steps
     const double rt = pow(press / P.C0, 1.0 / P.gamma);          // rho*theta
-    store_with_images(P, idR, k[u], j[u], i[u], rho - __ldg(P.hyc + k[u]));
-    store_with_images(P, idU, k[u], j[u], i[u], f5[u][1]);
-    store_with_images(P, idV, k[u], j[u], i[u], f5[u][2]);
-    store_with_images(P, idW, k[u], j[u], i[u], f5[u][3]);
-    store_with_images(P, idT, k[u], j[u], i[u], rt - __ldg(P.hytc + k[u]));
+    // all N values first, then the stores from one base address and ONE branch for the few cells that have images
+    double out[NUM_STATE + (NT > 0 ? NT : 1)];
+    out[idR] = rho - __ldg(P.hyc + k[u]);
+    out[idU] = f5[u][1]; out[idV] = f5[u][2]; out[idW] = f5[u][3];
+    out[idT] = rt - __ldg(P.hytc + k[u]);
     const double r = 1.0 / rho;
 #pragma unroll
-    for (int tr = 0; tr < NT; ++tr)
-      store_with_images(P, NUM_STATE + tr, k[u], j[u], i[u], trv[u][tr] * r);
+    for (int tr = 0; tr < NT; ++tr) out[NUM_STATE + tr] = trv[u][tr] * r;
+    double *cell = P.qout + ((long long) k[u] * P.zstride + (long long) (j[u] + HALO) * P.pitch + HALO + i[u]);
+#pragma unroll
+    for (int l = 0; l < NUM_STATE + NT; ++l) cell[(long long) l * P.vstride] = out[l];
+    const int m = image_mask(P, j[u], i[u]);
+    if (m) {
+      const int mf = m & P.ifast, ms = m & ~P.ifast;
+#pragma unroll
+      for (int l = 0; l < NUM_STATE + NT; ++l)
+        if (mf) store_images_fast(P, mf, cell + (long long) l * P.vstride, out[l]);
+      if (ms) {
+        double tmp[NUM_STATE + (NT > 0 ? NT : 1)];
+#pragma unroll
+        for (int l = 0; l < NUM_STATE + NT; ++l) tmp[l] = out[l];
+        store_images_cold(&P, ms, k[u], j[u], i[u], tmp, NUM_STATE + NT);
+      }
+    }
   }
 }
 

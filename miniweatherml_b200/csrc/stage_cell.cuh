@@ -77,19 +77,12 @@ __device__ __forceinline__ void face_flux(const double (&L)[N], const double (&R
 
 // Low edge values of n variables of one cell from global memory (stride st between the five stencil cells); out of line
 // and through local memory on purpose: only the MW_FBC_REF1 boundary faces call it (see phase 2 of the kernel)
-__device__ __noinline__ void ref1_low_edges(const double *q, long long st, long long vstride, int n, double *out) {
+static __device__ __noinline__ void ref1_low_edges(const double *q, long long st, long long vstride, int n, double *out) {
   for (int v = 0; v < n; ++v, q += vstride) {
     double lo, hi;
     weno5_edges(q[-2 * st], q[-st], q[0], q[st], q[2 * st], lo, hi);
     out[v] = lo;
   }
-}
-
-// The images of an edge cell's n state variables (periodic wrap, a neighbour rank's halo, boundary copies).  Out of line:
-// few threads have any, and inlined the address arithmetic of four destinations per variable adds 15 % to the kernel's
-// instruction footprint (measured: 5.14 -> 5.30 ms per launch at config 2 through instruction-cache misses).
-__device__ __noinline__ void store_images_cold(const StageParams *P, int mask, int k, int j, int i, const double *v, int n) {
-  for (int l = 0; l < n; ++l) store_images(*P, mask, l, k, j, i, v[l]);
 }
 
 // neighbour exchange along x inside a tile row (W = TX lanes)

@@ -234,18 +234,23 @@ def test_mlp_dense2_tensor_cores_vs_oracle(nin, nh, nout, B):
     ref = O.mlp_dense2(w, x, nh, nout, 0.1)
     y = mw.mlp_dense2_forward(w, torch.tensor(x, device="cuda"), nh, nout, 0.1, use_tensor_cores=True).cpu().numpy()
     assert np.isfinite(y).all()
-    # Both fp32 evaluations round differently (ponni sums in order, the tensor cores in tiles): the yardstick is the same
-    # network in fp64.  The tensor-core result must be within ponni's 1e-6 (scaled by the output magnitude) of the fp32
-    # oracle, or at least as close to the exact value as twice the oracle's own rounding error (wide layers: sums of 200+ terms)
+    # Both fp32 evaluations round differently (ponni sums in order, the tensor cores in tiles), so the yardstick is the
+    # same network in fp64.  Within ponni's 1e-6 of the fp32 oracle at the surrogate's widths; for the wide layers of the
+    # sweep (sums of 200+ products) within the error model of the 3xTF32 split: a product keeps 21 of fp32's 24 mantissa
+    # bits (the lo*lo term is dropped), i.e. 2^-21 of the sum of the magnitudes that enter an output, through both layers.
     W1 = w[:nin * nh].reshape(nin, nh).astype(np.float64); b1 = w[nin * nh:nin * nh + nh].astype(np.float64)
     W2 = w[nin * nh + nh:nin * nh + nh + nh * nout].reshape(nh, nout).astype(np.float64); b2 = w[-nout:].astype(np.float64)
-    h = W1.T @ x.astype(np.float64) + b1[:, None]
+    x64 = x.astype(np.float64)
+    h = W1.T @ x64 + b1[:, None]
     h = np.where(h < 0, 0.1 * h, h)
     exact = W2.T @ h + b2[:, None]
     scale = max(1.0, float(np.abs(ref).max()))
     assert np.abs(ref - exact).max() <= 2e-5 * scale            # the oracle itself is an fp32 evaluation of this network
-    err_tc, err_ref = np.abs(y - exact).max(), np.abs(ref - exact).max()
-    assert np.abs(y - ref).max() <= 2e-6 * scale or err_tc <= 2.0 * err_ref + 1e-6 * scale, (np.abs(y - ref).max(), err_tc, err_ref)
+    mag1 = np.abs(W1).T @ np.abs(x64) + np.abs(b1)[:, None]
+    mag2 = np.abs(W2).T @ (np.abs(h) + 2.0 ** -21 * mag1) + np.abs(b2)[:, None]
+    bound = 2.0 ** -21 * float((mag2 + np.abs(W2).T @ mag1).max())
+    err_tc = float(np.abs(y - exact).max())
+    assert np.abs(y - ref).max() <= 2e-6 * scale or err_tc <= bound, (np.abs(y - ref).max(), err_tc, bound)
     with pytest.raises(mw.MwError):
         mw.mlp_dense2_forward(np.zeros(17 * 2 + 2 + 2 + 1, dtype=np.float32), torch.zeros((17, 4), device="cuda"), 2, 1,
                               use_tensor_cores=True)
