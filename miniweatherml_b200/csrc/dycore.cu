@@ -89,6 +89,7 @@ struct mw_dycore {
   CUtensorMap tmap[3];
   CUtensorMap tmapI[3];                // cell kernel: interior box {32, 8, 1, N} of the same buffers (z windows)
   double *flux_x = nullptr, *flux_y = nullptr, *flux_z = nullptr, *mult = nullptr;
+  unsigned char *tflag = nullptr;      // [T][tile rows][tile columns]: the stage scaled a flux of that tile (StageParams::tflag)
   double *bg = nullptr;                // hyc[nz], hytc[nz], hye[nz+1], hyte[nz+1]
   std::vector<double> bg_host;
   bool bg_set = false;
@@ -150,6 +151,7 @@ static StageParams base_params(const mw_dycore *h) {
   P.nx = c.nx; P.ny = c.ny; P.nz = c.nz;
   P.pitch = h->pitch; P.zstride = h->zstride; P.vstride = h->vstride;
   P.flux_x = h->flux_x; P.flux_y = h->flux_y; P.flux_z = h->flux_z; P.mult = h->mult;
+  P.tflag = h->tflag; P.tf_nbx = (c.nx + TILE_X - 1) / TILE_X; P.tf_nby = (c.ny + TILE_Y - 1) / TILE_Y;
   P.hyc = h->bg; P.hytc = h->bg + c.nz; P.hye = h->bg + 2 * c.nz; P.hyte = h->bg + 3 * c.nz + 1;
   P.ihytc = h->bg + 4 * c.nz + 2; P.pcell = P.ihytc + c.nz; P.ihyte = P.pcell + c.nz; P.pedge = P.ihyte + c.nz + 1;
   P.pser[0] = 1.0;                                         // C(gamma, n)
@@ -285,6 +287,9 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   if (ce == cudaSuccess) ce = cudaMalloc(&h->flux_y, T * nzl * (nyl + 1) * nxl * 8);
   if (ce == cudaSuccess) ce = cudaMalloc(&h->flux_z, T * (nzl + 1) * nyl * nxl * 8);
   if (ce == cudaSuccess) ce = cudaMalloc(&h->mult, T * nzl * nyl * nxl * 8);
+  const size_t nflag = (size_t) T * ((nyl + TILE_Y - 1) / TILE_Y) * ((nxl + TILE_X - 1) / TILE_X);
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->tflag, nflag);
+  if (ce == cudaSuccess) ce = cudaMemset(h->tflag, 1, nflag);
   if (ce == cudaSuccess) ce = cudaMalloc(&h->bg, (8 * nzl + 4) * 8);
   if (ce != cudaSuccess) {
     set_error("mw_dycore_create: device allocation failed: %s", cudaGetErrorString(ce));
@@ -310,7 +315,7 @@ extern "C" int mw_dycore_destroy(mw_dycore *h) {
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(h->flags);
   for (int b = 0; b < 3; ++b) cudaFree(h->q[b]);
-  cudaFree(h->flux_x); cudaFree(h->flux_y); cudaFree(h->flux_z); cudaFree(h->mult); cudaFree(h->bg);
+  cudaFree(h->flux_x); cudaFree(h->flux_y); cudaFree(h->flux_z); cudaFree(h->mult); cudaFree(h->tflag); cudaFree(h->bg);
   if (h->dev_fields_alloc) for (int f = 0; f < h->N; ++f) cudaFree(h->dev_fields[f]);
   for (int d = 0; d < 4; ++d) { cudaFree(h->hsend[d]); cudaFree(h->hrecv[d]); cudaFree(h->msend[d]); cudaFree(h->mrecv[d]); }
   for (auto e : h->ev) cudaEventDestroy(e);

@@ -15,6 +15,7 @@
 namespace mw {
 
 constexpr int HALO = 3;
+constexpr int STAGE_TILE_X = 32, STAGE_TILE_Y = 8;    // the stage kernel's tile (CellCfg::TX, TY; dycore.cu: TILE_X, TILE_Y)
 constexpr int MW_FBC_REF1 = 3;
 enum { idR = 0, idU = 1, idV = 2, idW = 3, idT = 4, NUM_STATE = 5 };
 
@@ -28,6 +29,10 @@ struct StageParams {
   double *qout;              // stage output (dycore form, haloed); may alias q0 (stage 3)
   double *flux_x, *flux_y, *flux_z;   // tracer face fluxes [T][nz][ny][nx+1], [T][nz][ny+1][nx], [T][nz+1][ny][nx]
   double *mult;              // FCT scaling factor per tracer cell [T][nz][ny][nx]
+  // [T][tf_nby][tf_nbx] bytes, one per tracer and tile column of the stage kernel: non-zero when some factor of that tile
+  // is below one.  Almost everywhere the factors are all one, and the tracer finish then skips reading them.
+  unsigned char *tflag;
+  int tf_nbx, tf_nby;
   const double *hyc, *hytc, *hye, *hyte;   // background profiles (device)
   const double *ihytc, *pcell, *ihyte, *pedge;   // 1/hytc, C0*hytc^gamma (cells) and the same at the z edges
   double pser[12];           // binomial coefficients C(gamma,n), n = 0..11, of (1+e)^gamma
@@ -243,7 +248,20 @@ __device__ __forceinline__ void tracer_finish_cell(const StageParams &P, const C
       const double *FYp = P.flux_y + (((long long) tr * P.nz + k) * (P.ny + 1) + j) * P.nx + i;
       fyl = FYp[0]; fyh = FYp[P.nx];
     }
-    if ((P.positive_mask >> tr) & 1u) {
+    bool scaled = ((P.positive_mask >> tr) & 1u) != 0;
+    if (scaled) {
+      // a factor below one can reach my faces only from my own tile, the tiles next to it when I sit on its edge, or the
+      // neighbour rank (whose flags I do not have): otherwise every factor I would read is exactly one
+      const unsigned char *F = P.tflag + (long long) tr * P.tf_nby * P.tf_nbx;
+      const int tx = i / STAGE_TILE_X, ty = j / STAGE_TILE_Y, xi = i % STAGE_TILE_X, yj = j % STAGE_TILE_Y;
+      int f = F[ty * P.tf_nbx + tx];
+      if (xi == 0) f |= (i > 0) ? F[ty * P.tf_nbx + tx - 1] : (P.msrc[0].base != nullptr);
+      if (xi == STAGE_TILE_X - 1 || i == P.nx - 1) f |= (i < P.nx - 1) ? F[ty * P.tf_nbx + tx + 1] : (P.msrc[1].base != nullptr);
+      if (yj == 0) f |= (j > 0) ? F[(ty - 1) * P.tf_nbx + tx] : (P.msrc[2].base != nullptr);
+      if (yj == STAGE_TILE_Y - 1 || j == P.ny - 1) f |= (j < P.ny - 1) ? F[(ty + 1) * P.tf_nbx + tx] : (P.msrc[3].base != nullptr);
+      scaled = f != 0;
+    }
+    if (scaled) {
       const double ms = Mp[0];
       if (fxl > 0) { if (i > 0) fxl *= Mp[-1]; else if (P.msrc[0].base) fxl *= neighbour_mult(P, 0, tr, k, j); }             else if (fxl < 0) fxl *= ms;
       if (fxh < 0) { if (i < P.nx - 1) fxh *= Mp[1]; else if (P.msrc[1].base) fxh *= neighbour_mult(P, 1, tr, k, j); }       else if (fxh > 0) fxh *= ms;

@@ -22,7 +22,7 @@ namespace mw {
 template <int NT>
 struct CellCfg {
   static constexpr int N = NUM_STATE + NT, NV1 = N + 1;        // NV1: the variables plus the edge pressure
-  static constexpr int TX = 32, TY = 8, TT = TX * TY, NTHR = TT;
+  static constexpr int TX = STAGE_TILE_X, TY = STAGE_TILE_Y, TT = TX * TY, NTHR = TT;
   static constexpr int PX = TX + 2 * HALO, PY = TY + 2 * HALO, PLANE = PX * PY;
   static constexpr int HSLOT = N * PLANE, HSLOTP = ((HSLOT + 15) / 16) * 16, NHS = 2;   // haloed planes (x / y stencils)
   // interior planes (z windows): rows of IW = TX + 2 cells starting one cell left of the tile, so that the box's first
@@ -244,16 +244,21 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     p_hiz_prev = p_hi;
   }
 
+  unsigned limited = 0;                                      // bit tr: I scaled a flux of tracer tr somewhere in my column (FCT)
   const uint32_t bar_a = smem_u32(hbar);                     // the mbarriers: NHS haloed slots, then NIS interior slots
 #pragma unroll 1
   for (int k = 0; k < nz; ++k) {
     const double *Hk = sm + C::OFF_H + (k % NHS) * C::HSLOTP;
     const double hyc_k = __ldg(P.hyc + k), hytc_k = __ldg(P.hytc + k);
     const double ihytc_k = __ldg(P.ihytc + k), pcell_k = __ldg(P.pcell + k);
-    // q0 of my cell: issued first, consumed after the second barrier
+    // q0 of my cell, consumed after the second barrier: issued first where the registers allow it, else after the
+    // reconstructions (with two or more tracers the N values would sit in registers through the phase that spills)
     double q0v[N];
+    auto load_q0 = [&]() {
 #pragma unroll
-    for (int l = 0; l < N; ++l) q0v[l] = have_q0 ? (PTRS ? q0p[(long long) l * P.vstride] : P.q0[(long long) l * P.vstride + hcell]) : 0.0;
+      for (int l = 0; l < N; ++l) q0v[l] = have_q0 ? (PTRS ? q0p[(long long) l * P.vstride] : P.q0[(long long) l * P.vstride + hcell]) : 0.0;
+    };
+    if (PTRS) load_q0();
     double prop = 0.0;
     if (P.use_immersed && in_dom) prop = __ldg(P.immersed + gcell);
 
@@ -358,6 +363,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
       if (k + 4 < nz) plain_i(k + 4);
     }
 
+    if (!PTRS) load_q0();
     // ================= phase 2: face fluxes =================
     // Open / wall lateral boundaries (StageParams::fbc; never taken in a periodic run).  The reference on one rank leaves
     // the east / north boundary face with the periodic neighbour's outer state (MW_FBC_REF1): the low edge values of cell 0
@@ -520,7 +526,10 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
               const double foz = (fmax(fz_hi[l], 0.0) - fmin(fz_lo[l], 0.0)) * P.rdz;
               const double mass_out = (fox + foy + foz) * P.dt_stage * vol;
               const bool limit = mass_out > mass_available;     // rare (a nearly emptied cell): keep the division out of the common path
-              if (__any_sync(0xffffffffu, limit)) { if (limit) m = mass_available / mass_out; }
+              if (__any_sync(0xffffffffu, limit)) {
+                if (limit) m = mass_available / mass_out;
+                if (limit && in_dom && m < 1.0) limited |= 1u << tr;
+              }
             }
             if (in_dom) {
               P.mult[(long long) tr * nz * plane_cells + gcell] = m;
@@ -545,6 +554,12 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     for (int l = 0; l < N; ++l) fz_lo[l] = fz_hi[l];
     gcell += plane_cells;
     if (PTRS) { q0p += P.zstride; qop += P.zstride; } else hcell += P.zstride;
+  }
+  // the tile's FCT flags for the tracer finish (StageParams::tflag): written by every tile, scaled or not
+#pragma unroll
+  for (int tr = 0; tr < NT; ++tr) {
+    const int any = __syncthreads_or((limited >> tr) & 1u);
+    if (tid == 0) P.tflag[((long long) tr * P.tf_nby + tby) * P.tf_nbx + tbx] = (unsigned char) (any != 0);
   }
 }
 
