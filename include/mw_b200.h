@@ -59,7 +59,7 @@ typedef struct {
   double R_d, R_v, cp_d, p0, grav;    /* options set by micro/dycore init (KES:85-94, DYC:1227-1232)               */
   double C0, gamma_d;                 /* DYC:1242-1247                                                             */
   double earthrot, latitude;          /* fcor = 2*earthrot*sin(latitude) (DYC:213)                                 */
-  int    bc_x, bc_y, bc_z;            /* x, y: periodic, open or wall; bc_z: wall or open (periodic z is not implemented) */
+  int    bc_x, bc_y, bc_z;            /* each: periodic, open or wall (DYC:46-48); periodic bc_z needs nz >= 5             */
   int    enable_gravity;
   int    use_immersed_boundaries;
 } mw_config;

@@ -178,6 +178,7 @@ static StageParams base_params(const mw_dycore *h) {
     if ((d & 1) && P.fbc[d] && (d < 2 ? c.nproc_x : c.nproc_y) == 1 && !h->bc_both_faces) P.fbc[d] = MW_FBC_REF1;
     if (P.hbc[d]) P.bc_any = 1;
   }
+  if (c.bc_z == MW_BC_PERIODIC) P.bc_any = 1;            // the periodic z boundary also lives in the LBC instantiation of the stage kernel
   // FCT donors across interior rank boundaries (never across the global periodic seam, see StageParams)
   const bool interior[4] = {h->dir_active[0] && c.px > 0, h->dir_active[1] && c.px < c.nproc_x - 1,
                             h->dir_active[2] && c.py > 0, h->dir_active[3] && c.py < c.nproc_y - 1};
@@ -260,7 +261,8 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   MW_REQUIRE(cfg->num_tracers <= 4, "num_tracers = %d: stage kernel is instantiated for 0..4 tracers", cfg->num_tracers);
   for (int bc : {cfg->bc_x, cfg->bc_y})
     MW_REQUIRE(bc == MW_BC_PERIODIC || bc == MW_BC_OPEN || bc == MW_BC_WALL, "bc_x / bc_y must be periodic, open or wall");
-  MW_REQUIRE(cfg->bc_z == MW_BC_WALL || cfg->bc_z == MW_BC_OPEN, "bc_z must be wall or open");
+  MW_REQUIRE(cfg->bc_z == MW_BC_WALL || cfg->bc_z == MW_BC_OPEN || cfg->bc_z == MW_BC_PERIODIC, "bc_z must be periodic, open or wall");
+  MW_REQUIRE(cfg->bc_z != MW_BC_PERIODIC || cfg->nz >= 5, "periodic bc_z needs nz >= 5 (nz = %d)", cfg->nz);
   MW_REQUIRE(cfg->C0 > 0 && cfg->gamma_d > 1, "C0/gamma_d not set (call mw_config_defaults)");
   MW_REQUIRE((double) (cfg->nz + 1) * (cfg->ny + 1) * (cfg->nx + 1) < 2147483647.0, "block of %d x %d x %d cells: the face arrays are indexed with 32 bits",
              cfg->nx, cfg->ny, cfg->nz);
@@ -371,7 +373,8 @@ extern "C" int mw_dycore_set_immersed(mw_dycore *h, const double *immersed) {
 extern "C" int mw_dycore_update_options(mw_dycore *h, int enable_gravity, double grav, double latitude, double earthrot,
                                         double C0, double gamma_d, int bc_z) {
   MW_REQUIRE(h, "mw_dycore_update_options: null handle");
-  MW_REQUIRE(bc_z == MW_BC_WALL || bc_z == MW_BC_OPEN, "bc_z must be wall or open");
+  MW_REQUIRE(bc_z == MW_BC_WALL || bc_z == MW_BC_OPEN || bc_z == MW_BC_PERIODIC, "bc_z must be periodic, open or wall");
+  MW_REQUIRE(bc_z != MW_BC_PERIODIC || h->cfg.nz >= 5, "periodic bc_z needs nz >= 5 (nz = %d)", h->cfg.nz);
   MW_REQUIRE(C0 > 0 && gamma_d > 1, "mw_dycore_update_options: C0 = %g, gamma_d = %g", C0, gamma_d);
   mw_config &c = h->cfg;
   const bool eos_changed = (C0 != c.C0 || gamma_d != c.gamma_d);

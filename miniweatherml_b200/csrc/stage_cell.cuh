@@ -51,10 +51,12 @@ struct CellCfg {
 // (rho theta)', c_tr) on the low / high side, pL / pR their pressures, hy_r / hy_t the hydrostatic density and rho*theta
 // added back at this face, IDN the normal velocity.  The rho*theta flux keeps the association the round-1 kernels
 // used (x, y: (m* / rho_up) * rt, z: (m* * rt) / rho_up) so results stay bit-identical with the plain-load kernel.
+// face_flux_bg: the two sides carry their own background (the periodic z boundary: the top edge's on the left, the bottom
+// edge's on the right, DYC:1008-1019); face_flux is the common case of one background.
 template <int N, int IDN, bool ZDIR>
-__device__ __forceinline__ void face_flux(const double (&L)[N], const double (&R)[N], double pL, double pR, double hy_r,
-                                          double hy_t, double (&f)[N]) {
-  const double rL = L[idR] + hy_r, rR = R[idR] + hy_r;
+__device__ __forceinline__ void face_flux_bg(const double (&L)[N], const double (&R)[N], double pL, double pR, double hy_rL,
+                                             double hy_rR, double hy_tL, double hy_tR, double (&f)[N]) {
+  const double rL = L[idR] + hy_rL, rR = R[idR] + hy_rR;
   const double mL = L[IDN] * rL, mR = R[IDN] * rR;
   double m_upw, p_upw;
   bool upL;
@@ -67,6 +69,7 @@ __device__ __forceinline__ void face_flux(const double (&L)[N], const double (&R
     if (l == idR) v = m_upw;
     else {
       const double q_up = upL ? L[l] : R[l];
+      const double hy_t = upL ? hy_tL : hy_tR;
       if (l == idT) v = ZDIR ? (m_upw * (q_up + hy_t)) * rinv : mth * (q_up + hy_t);
       else v = m_upw * q_up;
       if (l == IDN) v += p_upw;
@@ -83,6 +86,12 @@ static __device__ __noinline__ void ref1_low_edges(const double *q, long long st
     weno5_edges(q[-2 * st], q[-st], q[0], q[st], q[2 * st], lo, hi);
     out[v] = lo;
   }
+}
+
+template <int N, int IDN, bool ZDIR>
+__device__ __forceinline__ void face_flux(const double (&L)[N], const double (&R)[N], double pL, double pR, double hy_r,
+                                          double hy_t, double (&f)[N]) {
+  face_flux_bg<N, IDN, ZDIR>(L, R, pL, pR, hy_r, hy_r, hy_t, hy_t, f);
 }
 
 // neighbour exchange along x inside a tile row (W = TX lanes)
@@ -115,10 +124,17 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     mbar_expect_tx(&hbar[lev % NHS], (uint32_t) (C::HSLOT * 8));
     tma_load_4d(sm + C::OFF_H + (lev % NHS) * C::HSLOTP, &tmapH, &hbar[lev % NHS], i0, j0, lev, 0);
   };
+  // Periodic z (LBC instantiation only, DYC:752-763): the z windows wrap, so interior planes are requested from level -3
+  // (= nz-3) up to nz+2 (= 2); slot and mbarrier phase of a level count from the first request.
+  const bool zper = LBC && P.bc_z == MW_BC_PERIODIC;
+  const int zo = zper ? 3 : 0;
+  auto zplane = [&](int lev) { return zper ? (lev + nz) % nz : lev; };
+  auto islot = [&](int lev) { return (lev + zo) % NIS; };
+  auto ipar = [&](int lev) { return (uint32_t) (((lev + zo) / NIS) & 1); };
   auto load_i = [&](int lev) {                               // interior plane of level lev (thread 0 only)
     fence_proxy_async();
-    mbar_expect_tx(&ibar[lev % NIS], (uint32_t) (C::ISLOT * 8));
-    tma_load_4d(sm + C::OFF_I + (lev % NIS) * C::ISLOT, &tmapI, &ibar[lev % NIS], i0 + HALO - C::IXO, j0 + HALO, lev, 0);
+    mbar_expect_tx(&ibar[islot(lev)], (uint32_t) (C::ISLOT * 8));
+    tma_load_4d(sm + C::OFF_I + islot(lev) * C::ISLOT, &tmapI, &ibar[islot(lev)], i0 + HALO - C::IXO, j0 + HALO, zplane(lev), 0);
   };
   // MW_NO_TMA=1 (tests): the same boxes filled with plain loads by all threads, zero outside the arrays like TMA; the
   // CTA barriers of the level loop order them, so the mbarrier waits are skipped
@@ -132,24 +148,25 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     }
   };
   auto plain_i = [&](int lev) {
-    double *dst = sm + C::OFF_I + (lev % NIS) * C::ISLOT;
+    double *dst = sm + C::OFF_I + islot(lev) * C::ISLOT;
     for (int idx = tid; idx < C::ISLOT; idx += C::NTHR) {
       const int l = idx / IPL, c = idx % IPL, jh = j0 + HALO + c / C::IW, ih = i0 + HALO - C::IXO + c % C::IW;
       dst[idx] = (jh < P.ny + 2 * HALO && ih < P.pitch)
-                     ? P.qin[(long long) l * P.vstride + (long long) lev * P.zstride + (long long) jh * P.pitch + ih] : 0.0;
+                     ? P.qin[(long long) l * P.vstride + (long long) zplane(lev) * P.zstride + (long long) jh * P.pitch + ih] : 0.0;
     }
   };
+  const int nfirst = zper ? NIS : 4;                         // interior planes requested up front: levels -zo .. -zo + nfirst - 1
   if (use_tma) {
     if (tid == 0) {
       for (int s = 0; s < NHS + NIS; ++s) mbar_init(&hbar[s], 1);
       mbar_fence_init();
       tma_prefetch_desc(&tmapH);
       tma_prefetch_desc(&tmapI);
-      for (int lev = 0; lev < 4 && lev < nz; ++lev) load_i(lev);
+      for (int lev = -zo; lev < nfirst - zo && lev < nz; ++lev) load_i(lev);
       for (int lev = 0; lev < NHS && lev < nz; ++lev) load_h(lev);
     }
   } else {
-    for (int lev = 0; lev < 4 && lev < nz; ++lev) plain_i(lev);
+    for (int lev = -zo; lev < nfirst - zo && lev < nz; ++lev) plain_i(lev);
     for (int lev = 0; lev < NHS && lev < nz; ++lev) plain_h(lev);
   }
 
@@ -197,12 +214,13 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
   // condition (DYC:752-781): copy the nearest interior level, a wall zeroes w
   const double *Ibase = sm + C::OFF_I + y * C::IW + x + C::IXO;
   auto zslot = [&](int lev) -> const double * {
-    const int lc = lev < 0 ? 0 : (lev >= nz ? nz - 1 : lev);
-    return Ibase + (lc % NIS) * C::ISLOT;
+    const int lc = zper ? lev : (lev < 0 ? 0 : (lev >= nz ? nz - 1 : lev));
+    return Ibase + islot(lc) * C::ISLOT;
   };
   double hiz_prev[N], p_hiz_prev, fz_lo[N];
-  // z reconstruction of level kc -> lo / hi edge values and pressures (edge profiles kc and kc + 1)
-  auto zrecon = [&](int kc, double (&lo)[N], double (&hi)[N], double &p_lo, double &p_hi, int &big) {
+  // z reconstruction of level kc -> lo / hi edge values and pressures (edge profiles kb and kb + 1; kb = kc except for the
+  // wrapped levels of a periodic z boundary, whose background is that of the level they are an image of)
+  auto zrecon = [&](int kc, int kb, double (&lo)[N], double (&hi)[N], double &p_lo, double &p_hi, int &big) {
     const double *w0 = zslot(kc - 2), *w1 = zslot(kc - 1), *w2 = zslot(kc), *w3 = zslot(kc + 1), *w4 = zslot(kc + 2);
     const bool z0 = wall && kc - 2 < 0, z1 = wall && kc - 1 < 0, z3 = wall && kc + 1 >= nz, z4 = wall && kc + 2 >= nz;
 #pragma unroll
@@ -211,8 +229,8 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
       if (v == idW) { if (z0) a0 = 0.0; if (z1) a1 = 0.0; if (z3) a3 = 0.0; if (z4) a4 = 0.0; }
       weno5_edges(a0, a1, a2, a3, a4, lo[v], hi[v]);
     }
-    p_lo = eos_pressure_series(lo[idT], __ldg(P.ihyte + kc), __ldg(P.pedge + kc), P, big);
-    p_hi = eos_pressure_series(hi[idT], __ldg(P.ihyte + kc + 1), __ldg(P.pedge + kc + 1), P, big);
+    p_lo = eos_pressure_series(lo[idT], __ldg(P.ihyte + kb), __ldg(P.pedge + kb), P, big);
+    p_hi = eos_pressure_series(hi[idT], __ldg(P.ihyte + kb + 1), __ldg(P.pedge + kb + 1), P, big);
   };
   // |rt'/rt_bg| > 0.1 somewhere (never in the shipped cases): redo those pressures with the exact pow()
   auto eos_repair = [&](double rtp, double bg, double &p) {
@@ -228,11 +246,32 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
   __syncthreads();                                           // barriers initialised
 
   // ---- prologue: level 0 in z and the bottom boundary face (DYC:1020-1038: both sides mirrored, w = 0 at a wall) ----
-  if (use_tma) for (int lev = 0; lev < 3 && lev < nz; ++lev) mbar_wait_spin(&ibar[lev % NIS], 0u);
-  {
+  if (zper) {
+    // periodic z: the face below level 0 is the face above level nz-1 -- left state = high edge of level -1 (= nz-1) with
+    // the background of edge nz, right state = low edge of level 0 with the background of edge 0
+    if (use_tma) for (int lev = -3; lev < 2; ++lev) mbar_wait_spin(&ibar[islot(lev)], 0u);
+    double lo[N], hi[N], Lp[N], p_lo, p_hi, p_Lp;
+    int big = 0;
+    zrecon(-1, nz - 1, lo, Lp, p_lo, p_Lp, big);
+    if (big) eos_repair(Lp[idT], __ldg(P.hyte + nz), p_Lp);
+    __syncthreads();                                         // level -3 is dead: its slot takes level 2
+    if (use_tma) { if (tid == 0) load_i(2); mbar_wait_spin(&ibar[islot(2)], ipar(2)); }
+    else { plain_i(2); __syncthreads(); }
+    big = 0;
+    zrecon(0, 0, lo, hi, p_lo, p_hi, big);
+    if (big) { eos_repair(lo[idT], __ldg(P.hyte), p_lo); eos_repair(hi[idT], __ldg(P.hyte + 1), p_hi); }
+    face_flux_bg<N, idW, true>(Lp, lo, p_Lp, p_lo, __ldg(P.hye + nz), __ldg(P.hye), __ldg(P.hyte + nz), __ldg(P.hyte), fz_lo);
+    store_flux_z(fz_lo, gcell);
+#pragma unroll
+    for (int v = 0; v < N; ++v) hiz_prev[v] = hi[v];
+    p_hiz_prev = p_hi;
+    __syncthreads();                                         // level -2 is dead: its slot takes level 3
+    if (use_tma) { if (tid == 0) load_i(3); } else plain_i(3);
+  } else {
+    if (use_tma) for (int lev = 0; lev < 3 && lev < nz; ++lev) mbar_wait_spin(&ibar[lev % NIS], 0u);
     double lo[N], hi[N], p_lo, p_hi;
     int big = 0;
-    zrecon(0, lo, hi, p_lo, p_hi, big);
+    zrecon(0, 0, lo, hi, p_lo, p_hi, big);
     if (big) { eos_repair(lo[idT], __ldg(P.hyte), p_lo); eos_repair(hi[idT], __ldg(P.hyte + 1), p_hi); }
     double Lb[N];
 #pragma unroll
@@ -265,10 +304,10 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     if (use_tma) {
       if (PTRS) {                                            // (the out-of-line polling loop costs registers too)
         mbar_wait_fast(bar_a + 8u * (uint32_t) (k % NHS), (uint32_t) ((k / NHS) & 1));
-        if (k + 3 < nz) mbar_wait_fast(bar_a + 8u * (uint32_t) (NHS + (k + 3) % NIS), (uint32_t) (((k + 3) / NIS) & 1));
+        if (k + 3 < nz + zo) mbar_wait_fast(bar_a + 8u * (uint32_t) (NHS + islot(k + 3)), ipar(k + 3));
       } else {
         mbar_wait_spin(&hbar[k % NHS], (uint32_t) ((k / NHS) & 1));
-        if (k + 3 < nz) mbar_wait_spin(&ibar[(k + 3) % NIS], (uint32_t) (((k + 3) / NIS) & 1));
+        if (k + 3 < nz + zo) mbar_wait_spin(&ibar[islot(k + 3)], ipar(k + 3));
       }
     }
 
@@ -315,14 +354,15 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     p_lox = eos_pressure_series(lox[idT], ihytc_k, pcell_k, P, big);
     p_hix = eos_pressure_series(hix[idT], ihytc_k, pcell_k, P, big);
     // ---- z: level k+1 (clamped to the top level: its values are replaced by the boundary state below) ----
-    const bool top = (k + 1 >= nz);
-    const int kz = top ? nz - 1 : k + 1;
+    const bool ptop = zper && k + 1 >= nz;                   // periodic z: the level above the top one is level 0, background included
+    const bool top = !zper && (k + 1 >= nz);
+    const int kz = top ? nz - 1 : k + 1, kbz = ptop ? 0 : kz;
     double loz[N], hiz[N], p_loz, p_hiz;
-    zrecon(kz, loz, hiz, p_loz, p_hiz, big);
+    zrecon(kz, kbz, loz, hiz, p_loz, p_hiz, big);
     if (big) {                                               // rare: exact pressures where the series does not apply
       eos_repair(loy[idT], hytc_k, p_loy); eos_repair(hiy[idT], hytc_k, p_hiy);
       eos_repair(lox[idT], hytc_k, p_lox); eos_repair(hix[idT], hytc_k, p_hix);
-      eos_repair(loz[idT], __ldg(P.hyte + kz), p_loz); eos_repair(hiz[idT], __ldg(P.hyte + kz + 1), p_hiz);
+      eos_repair(loz[idT], __ldg(P.hyte + kbz), p_loz); eos_repair(hiz[idT], __ldg(P.hyte + kbz + 1), p_hiz);
       if (big & 2) eos_repair(ring_e[0], hytc_k, ring_p);
     }
     // publish: y edge values of my cell, ring edge values
@@ -346,7 +386,8 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
         Lz[v] = (top && v == idW && wall) ? 0.0 : hiz_prev[v];
         Rz[v] = top ? Lz[v] : loz[v];
       }
-      face_flux<N, idW, true>(Lz, Rz, p_hiz_prev, top ? p_hiz_prev : p_loz, he, hte, fz_hi);
+      if (LBC && ptop) face_flux_bg<N, idW, true>(Lz, Rz, p_hiz_prev, p_loz, he, __ldg(P.hye), hte, __ldg(P.hyte), fz_hi);
+      else face_flux<N, idW, true>(Lz, Rz, p_hiz_prev, top ? p_hiz_prev : p_loz, he, hte, fz_hi);
       store_flux_z(fz_hi, gcell + plane_cells);
 #pragma unroll
       for (int v = 0; v < N; ++v) hiz_prev[v] = hiz[v];
@@ -356,11 +397,11 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     if (use_tma) {
       if (tid == 0) {
         if (k + NHS < nz) load_h(k + NHS);
-        if (k + 4 < nz) load_i(k + 4);
+        if (k + 4 < nz + zo) load_i(k + 4);
       }
     } else {
       if (k + NHS < nz) plain_h(k + NHS);
-      if (k + 4 < nz) plain_i(k + 4);
+      if (k + 4 < nz + zo) plain_i(k + 4);
     }
 
     if (!PTRS) load_q0();
@@ -473,7 +514,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
 #pragma unroll
         for (int v = 0; v < N; ++v) fy_hi[v] = FY[(v * (TY + 1) + y + 1) * TX + x];
       }
-      const double *Ik = Ibase + (k % NIS) * C::ISLOT;      // my cell at level k
+      const double *Ik = Ibase + islot(k) * C::ISLOT;       // my cell at level k
       const double rho_k = Ik[idR * IPL] + hyc_k;
       const double u_k = Ik[idU * IPL], v_k = Ik[idV * IPL];
       const double rho0 = q0v[idR] + hyc_k;
