@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MW_MAX_TRACERS 8
+#define MW_MAX_TRACERS 50               /* model/core/MultipleFields.h:11 */
 
 typedef enum {
   MW_OK = 0,

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-MAX_TRACERS = 8
+MAX_TRACERS = 50
 BC_PERIODIC, BC_OPEN, BC_WALL = 0, 1, 2
 
 

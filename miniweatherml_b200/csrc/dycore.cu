@@ -166,7 +166,7 @@ static StageParams base_params(const mw_dycore *h) {
   P.enable_gravity = c.enable_gravity;
   P.use_immersed = (c.use_immersed_boundaries && h->immersed) ? 1 : 0;
   unsigned pm = 0;
-  for (int t = 0; t < c.num_tracers; ++t) if (c.tracer_positive[t]) pm |= 1u << t;
+  for (int t = 0; t < c.num_tracers && t < 32; ++t) if (c.tracer_positive[t]) pm |= 1u << t;   // (groups: see group_params)
   P.positive_mask = pm;
   P.use_tma = h->use_tma;
   P.tile_mode = 0;
@@ -258,7 +258,6 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   MW_REQUIRE(cfg->nx >= HALO && cfg->nz >= 2 && cfg->ny >= 1, "grid too small (nx=%d ny=%d nz=%d)", cfg->nx, cfg->ny, cfg->nz);
   MW_REQUIRE(cfg->ny_glob == 1 || cfg->ny >= HALO, "ny = %d too small for a 3-D run", cfg->ny);
   MW_REQUIRE(cfg->num_tracers >= 0 && cfg->num_tracers <= MW_MAX_TRACERS, "num_tracers = %d out of range", cfg->num_tracers);
-  MW_REQUIRE(cfg->num_tracers <= 4, "num_tracers = %d: stage kernel is instantiated for 0..4 tracers", cfg->num_tracers);
   for (int bc : {cfg->bc_x, cfg->bc_y})
     MW_REQUIRE(bc == MW_BC_PERIODIC || bc == MW_BC_OPEN || bc == MW_BC_WALL, "bc_x / bc_y must be periodic, open or wall");
   MW_REQUIRE(cfg->bc_z == MW_BC_WALL || cfg->bc_z == MW_BC_OPEN || cfg->bc_z == MW_BC_PERIODIC, "bc_z must be periodic, open or wall");
@@ -276,6 +275,7 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
   h->qbytes = (size_t) h->N * h->vstride * sizeof(double);
   const char *e = getenv("MW_NO_TMA");
   h->use_tma = (e && atoi(e) != 0) ? 0 : 1;
+  if (cfg->num_tracers > 4) h->use_tma = 0;                // tracer groups (step_groups) run the plain-load instantiation
   e = getenv("MW_BC_BOTH_FACES");
   h->bc_both_faces = e && atoi(e) != 0;
   const int T = cfg->num_tracers > 0 ? cfg->num_tracers : 1;
@@ -298,7 +298,7 @@ extern "C" int mw_dycore_create(const mw_config *cfg, mw_dycore **out) {
     mw_dycore_destroy(h);
     return MW_ERR_CUDA;
   }
-  for (int b = 0; b < 3; ++b) {
+  for (int b = 0; b < 3 && cfg->num_tracers <= 4; ++b) {
     const uint64_t dims[4] = {(uint64_t) h->pitch, (uint64_t) (cfg->ny + 2 * HALO), (uint64_t) cfg->nz, (uint64_t) h->N};
     const uint64_t str[3] = {(uint64_t) h->pitch * 8, (uint64_t) h->zstride * 8, (uint64_t) h->vstride * 8};
     const uint32_t box[4] = {TILE_X + 2 * HALO, TILE_Y + 2 * HALO, 1, (uint32_t) h->N};
@@ -714,6 +714,111 @@ static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaSt
   return MW_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// More than four tracers (MultipleFields.h:11 allows 50).  The kernels are instantiated for 0..4 tracers -- the cell
+// kernel keeps every variable of a cell in registers -- so a stage is launched once per GROUP of up to four tracers: each
+// launch recomputes the state's reconstructions and fluxes (the tracers are advected by the state's mass flux) and
+// handles its own tracers; only the last one stores the state.  Plain-load instantiation (the TMA boxes cover contiguous
+// variables), run-time-T conversion kernels, no slab pipeline.  Correctness first: a step with T tracers costs about
+// ceil(T/4) steps with four.
+// ---------------------------------------------------------------------------------------------------------------------
+static StageParams group_params(const mw_dycore *h, const StageParams &P, int tr0, int nt, bool last) {
+  const mw_config &c = h->cfg;
+  StageParams G = P;
+  const long long nz = c.nz, ny = c.ny, nx = c.nx;
+  G.tr0 = tr0; G.skip_state = last ? 0 : 1;
+  G.bc_any = 1;                                            // selects the instantiation that knows tr0 / skip_state
+  G.flux_x += (long long) tr0 * nz * ny * (nx + 1);
+  G.flux_y += (long long) tr0 * nz * (ny + 1) * nx;
+  G.flux_z += (long long) tr0 * (nz + 1) * ny * nx;
+  G.mult += (long long) tr0 * nz * ny * nx;
+  G.tflag += (long long) tr0 * G.tf_nby * G.tf_nbx;
+  unsigned pm = 0;
+  for (int t = 0; t < nt; ++t) if (c.tracer_positive[tr0 + t]) pm |= 1u << t;
+  G.positive_mask = pm;
+  for (int d = 0; d < 4; ++d) if (G.msrc[d].base) G.msrc[d].base += (long long) tr0 * G.msrc[d].st_t;
+  return G;
+}
+template <int NT> static int launch_group_stage(mw_dycore *h, const StageParams &G, int in_buf, cudaStream_t st) {
+  using K = StageKernel<NT>;
+  static bool attr_set = false;
+  if (!attr_set) { MW_CUDA_OK(K::attr()); attr_set = true; }
+  K::launch(dim3((G.nx + K::TX - 1) / K::TX, (G.ny + 7) / 8), st, h, in_buf, G);
+  MW_CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return MW_OK;
+}
+static int step_groups(mw_dycore *h, double *const *fields, double dt_phys, cudaStream_t st) {
+  const mw_config &c = h->cfg;
+  const int T = c.num_tracers, ngroups = (T + 3) / 4;
+  const long long ncell = (long long) c.nz * c.ny * c.nx;
+  const unsigned cgrid = (unsigned) ((ncell + 255) / 256);
+  MW_REQUIRE(!h->overlap, "more than four tracers: MW_OVERLAP is not supported");
+  ConvertParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.S = base_params(h);
+  for (int f = 0; f < h->N; ++f) Q.fields[f] = fields[f];
+  Q.R_d = c.R_d; Q.R_v = c.R_v; Q.idWV = c.idWV;
+  for (int t = 0; t < T; ++t) if (c.tracer_adds_mass[t]) Q.adds_mass_mask64 |= 1ull << t;
+  h->n_stage_timed = 0;
+  if (h->timing) { while (h->ev.size() < 2) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); } cudaEventRecord(h->ev[0], st); }
+  Q.S.qout = h->q[0];
+  set_images(h, Q.S, 0);
+  k_coupler_to_dyn_rt<<<cgrid, 256, 0, st>>>(Q, T);
+  MW_CUDA_OK(cudaGetLastError());
+  h->launches++;
+  int rc = exchange_halos(h, h->q[0], st);
+  if (rc != MW_OK) return rc;
+  double dt_dyn = mw_dycore_compute_time_step(h);
+  const int ncycles = (int) ceil(dt_phys / dt_dyn);                        // DYC:104-108
+  dt_dyn = dt_phys / ncycles;
+  for (int ic = 0; ic < ncycles; ++ic) {
+    for (int s = 0; s < 3; ++s) {
+      StageParams P = base_params(h);
+      int in_buf;
+      if (s == 0)      { in_buf = 0; P.qout = h->q[1]; P.rk_a = 0.0;     P.rk_b = 1.0;     P.rk_cdt = dt_dyn;               P.dt_stage = dt_dyn; }
+      else if (s == 1) { in_buf = 1; P.qout = h->q[2]; P.rk_a = 3. / 4.; P.rk_b = 1. / 4.; P.rk_cdt = (1. / 4.) * dt_dyn;   P.dt_stage = (1. / 4.) * dt_dyn; }
+      else             { in_buf = 2; P.qout = h->q[0]; P.rk_a = 1. / 3.; P.rk_b = 2. / 3.; P.rk_cdt = (2. / 3.) * dt_dyn;   P.dt_stage = (2. / 3.) * dt_dyn; }
+      P.qin = h->q[in_buf];
+      P.q0 = h->q[0];
+      set_images(h, P, (in_buf + 1) % 3);
+      for (int g = 0; g < ngroups; ++g) {
+        const int tr0 = 4 * g, nt = std::min(4, T - tr0);
+        const StageParams G = group_params(h, P, tr0, nt, g == ngroups - 1);
+        switch (nt) {
+          case 1: rc = launch_group_stage<1>(h, G, in_buf, st); break;
+          case 2: rc = launch_group_stage<2>(h, G, in_buf, st); break;
+          case 3: rc = launch_group_stage<3>(h, G, in_buf, st); break;
+          default: rc = launch_group_stage<4>(h, G, in_buf, st); break;
+        }
+        if (rc != MW_OK) return rc;
+      }
+      rc = exchange_mult(h, st);                           // every tracer's boundary factors (NCCL) / the neighbour barrier (peer memory)
+      if (rc != MW_OK) return rc;
+      for (int g = 0; g < ngroups; ++g) {
+        const int tr0 = 4 * g, nt = std::min(4, T - tr0);
+        const StageParams G = group_params(h, P, tr0, nt, true);
+        switch (nt) {
+          case 1: k_tracer_update<1><<<cgrid, 256, 0, st>>>(G); break;
+          case 2: k_tracer_update<2><<<cgrid, 256, 0, st>>>(G); break;
+          case 3: k_tracer_update<3><<<cgrid, 256, 0, st>>>(G); break;
+          default: k_tracer_update<4><<<cgrid, 256, 0, st>>>(G); break;
+        }
+        MW_CUDA_OK(cudaGetLastError());
+        h->launches++;
+      }
+      rc = exchange_halos(h, P.qout, st);
+      if (rc != MW_OK) return rc;
+    }
+  }
+  Q.S.qin = h->q[0];
+  k_dyn_to_coupler_rt<<<cgrid, 256, 0, st>>>(Q, T);
+  MW_CUDA_OK(cudaGetLastError());
+  h->launches++;
+  if (h->timing) cudaEventRecord(h->ev[1], st);
+  return MW_OK;
+}
+
 extern "C" int mw_dycore_time_step(mw_dycore *h, double *const *fields, double dt_phys, void *stream) {
   MW_REQUIRE(h && fields, "mw_dycore_time_step: null argument");
   MW_REQUIRE(h->bg_set, "mw_dycore_time_step: background profiles not set");
@@ -727,8 +832,7 @@ extern "C" int mw_dycore_time_step(mw_dycore *h, double *const *fields, double d
     case 3: return step_impl<3>(h, fields, dt_phys, st);
     case 4: return step_impl<4>(h, fields, dt_phys, st);
   }
-  set_error("unsupported num_tracers");
-  return MW_ERR_INVALID;
+  return step_groups(h, fields, dt_phys, st);              // 5 .. MW_MAX_TRACERS tracers
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -990,7 +1094,7 @@ extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields
   const bool equal_blocks = c.nproc_x * c.nproc_y == 1 ||
                             (h->comm && c.nx_glob % c.nproc_x == 0 && c.ny_glob % c.nproc_y == 0 && c.nx == c.nx_glob / c.nproc_x && c.ny == c.ny_glob / c.nproc_y);
   const bool periodic_xy = c.bc_x == MW_BC_PERIODIC && c.bc_y == MW_BC_PERIODIC;     // the slab schedule wraps around the seam
-  const bool pipelined = rows_per_slab >= 8 && equal_blocks && periodic_xy && c.ny_glob > 1 && c.ny / rows_per_slab >= 4;
+  const bool pipelined = rows_per_slab >= 8 && equal_blocks && periodic_xy && c.num_tracers <= 4 && c.ny_glob > 1 && c.ny / rows_per_slab >= 4;
   if (pipelined) {
     MW_CUDA_OK(cudaDeviceSynchronize());                  // the non-blocking streams do not order against earlier default-stream work
     int rc = 1;

@@ -67,6 +67,12 @@ struct StageParams {
   // on both sides; MW_FBC_REF1 (E, N only): the reference on ONE rank in that direction, whose `else if` (DYC:1051, :1072)
   // leaves the face with the periodic neighbour's outer state, i.e. the low edge values of cell 0 of the row / column.
   int hbc[4], fbc[4], bc_any;
+  // More than four tracers: the kernels are instantiated for 0..4, so a stage is launched once per GROUP of up to four
+  // tracers (dycore.cu: step_groups).  A group launch sees its tracers as 0..nt-1: flux / factor / flag pointers and the
+  // positive mask are offset on the host, and the tracer variables of the haloed registers start tr0 variables further.
+  // skip_state: every group launch recomputes the state, only the last one stores it (the others would overwrite q0
+  // in the in-place third stage before the remaining groups have read it).
+  int tr0, skip_state;
   unsigned positive_mask;    // bit tr set <=> tracer tr must stay non-negative
   int use_tma;
   // which tiles a launch covers (halo exchange overlapped with interior compute): 0 = all (2-D grid), 1 = the interior
@@ -223,6 +229,7 @@ struct ConvertParams {
   double R_d, R_v;
   int idWV;
   unsigned adds_mass_mask;
+  unsigned long long adds_mass_mask64;             // the same for the run-time tracer count of the *_rt kernels
 };
 
 // D2C = true (last stage of a step): the dycore -> coupler conversion of the cell (DYC:1891-1951, k_dyn_to_coupler below)
@@ -271,10 +278,10 @@ __device__ __forceinline__ void tracer_finish_cell(const StageParams &P, const C
       if (fzh < 0) { if (k < P.nz - 1) fzh *= Mp[pl]; }          else if (fzh > 0) fzh *= ms;
     }
     const double t = -(fxh - fxl) * P.rdx - (fyh - fyl) * P.rdy - (fzh - fzl) * P.rdz;
-    double qn = P.qout[(long long) (NUM_STATE + tr) * P.vstride + hcell] + P.rk_cdt * t;
+    double qn = P.qout[(long long) (NUM_STATE + tr + P.tr0) * P.vstride + hcell] + P.rk_cdt * t;
     if ((P.positive_mask >> tr) & 1u) qn = fmax(0.0, qn);
     const double conc = qn / rho_new;                    // IEEE division: keeps the tracer-mass round trip unbiased
-    store_with_images(P, NUM_STATE + tr, k, j, i, conc);
+    store_with_images(P, NUM_STATE + tr + P.tr0, k, j, i, conc);
     if (D2C) tr_mass[tr] = conc * rho_new;
   }
   if (D2C) {
@@ -406,6 +413,53 @@ __global__ void __launch_bounds__(256) k_dyn_to_coupler(const ConvertParams Q) {
     Q.fields[3][c[u]] = qv[u][idW];
     Q.fields[4][c[u]] = press / (rho_d * Q.R_d + rho_v * Q.R_v);
   }
+}
+
+// The same conversions for a run-time tracer count (more than four tracers, dycore.cu: step_groups): one cell per
+// thread, loops over the tracers; same formulas.
+__global__ void __launch_bounds__(256) k_coupler_to_dyn_rt(const __grid_constant__ ConvertParams Q, int T) {
+  const StageParams &P = Q.S;
+  int i, j, k;
+  long long c;
+  if (!range_cell(P, k, j, i, c)) return;
+  const double rho_d = __ldg(Q.fields[0] + c), temp = __ldg(Q.fields[4] + c);
+  double rho = rho_d, rho_v = 0.0;
+  for (int tr = 0; tr < T; ++tr) {
+    const double m = __ldg(Q.fields[NUM_STATE + tr] + c);
+    if ((Q.adds_mass_mask64 >> tr) & 1ull) rho += m;
+    if (tr == Q.idWV) rho_v = m;
+  }
+  const double press = rho_d * Q.R_d * temp + rho_v * Q.R_v * temp;
+  const double rt = pow(press / P.C0, 1.0 / P.gamma);
+  store_with_images(P, idR, k, j, i, rho - __ldg(P.hyc + k));
+  store_with_images(P, idU, k, j, i, __ldg(Q.fields[1] + c));
+  store_with_images(P, idV, k, j, i, __ldg(Q.fields[2] + c));
+  store_with_images(P, idW, k, j, i, __ldg(Q.fields[3] + c));
+  store_with_images(P, idT, k, j, i, rt - __ldg(P.hytc + k));
+  const double r = 1.0 / rho;
+  for (int tr = 0; tr < T; ++tr) store_with_images(P, NUM_STATE + tr, k, j, i, __ldg(Q.fields[NUM_STATE + tr] + c) * r);
+}
+__global__ void __launch_bounds__(256) k_dyn_to_coupler_rt(const __grid_constant__ ConvertParams Q, int T) {
+  const StageParams &P = Q.S;
+  int i, j, k;
+  long long c;
+  if (!range_cell(P, k, j, i, c)) return;
+  const double *q = P.qin + ((long long) k * P.zstride + (long long) (j + HALO) * P.pitch + i + HALO);
+  const double rho = q[(long long) idR * P.vstride] + __ldg(P.hyc + k);
+  const double rt = q[(long long) idT * P.vstride] + __ldg(P.hytc + k);
+  const double press = P.C0 * pow(rt, P.gamma);
+  double rho_d = rho, rho_v = 0.0;
+  for (int tr = 0; tr < T; ++tr) {
+    const double m = q[(long long) (NUM_STATE + tr) * P.vstride] * rho;
+    Q.fields[NUM_STATE + tr][c] = m;
+    if ((Q.adds_mass_mask64 >> tr) & 1ull) rho_d -= m;
+    if (tr == Q.idWV) rho_v = m;
+  }
+  Q.fields[0][c] = rho_d;
+  Q.fields[1][c] = q[(long long) idU * P.vstride];
+  Q.fields[2][c] = q[(long long) idV * P.vstride];
+  Q.fields[3][c] = q[(long long) idW * P.vstride];
+  Q.fields[4][c] = press / (rho_d * Q.R_d + rho_v * Q.R_v);
 }
 
 // --------------------------------------------------------------------------------------------------------

@@ -80,8 +80,9 @@ __device__ __forceinline__ void face_flux_bg(const double (&L)[N], const double 
 
 // Low edge values of n variables of one cell from global memory (stride st between the five stencil cells); out of line
 // and through local memory on purpose: only the MW_FBC_REF1 boundary faces call it (see phase 2 of the kernel)
-static __device__ __noinline__ void ref1_low_edges(const double *q, long long st, long long vstride, int n, double *out) {
+static __device__ __noinline__ void ref1_low_edges(const double *q, long long st, long long vstride, long long troff, int n, double *out) {
   for (int v = 0; v < n; ++v, q += vstride) {
+    if (v == NUM_STATE) q += troff;                          // tracer group of a run with more than four tracers
     double lo, hi;
     weno5_edges(q[-2 * st], q[-st], q[0], q[st], q[2 * st], lo, hi);
     out[v] = lo;
@@ -126,6 +127,11 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
   };
   // Periodic z (LBC instantiation only, DYC:752-763): the z windows wrap, so interior planes are requested from level -3
   // (= nz-3) up to nz+2 (= 2); slot and mbarrier phase of a level count from the first request.
+  // A group launch of a run with more than four tracers (LBC instantiation, plain loads; StageParams::tr0): my tracer
+  // variables sit tr0 variables further in the haloed registers, and only the last group stores the state
+  const long long troff = LBC ? (long long) P.tr0 * P.vstride : 0;
+  const bool put_state = !LBC || !P.skip_state;
+  auto voff = [&](int l) { return (long long) l * P.vstride + (l >= NUM_STATE ? troff : 0); };
   const bool zper = LBC && P.bc_z == MW_BC_PERIODIC;
   const int zo = zper ? 3 : 0;
   auto zplane = [&](int lev) { return zper ? (lev + nz) % nz : lev; };
@@ -144,7 +150,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     for (int idx = tid; idx < C::HSLOT; idx += C::NTHR) {
       const int l = idx / PLANE, c = idx % PLANE, jh = j0 + c / PX, ih = i0 + c % PX;
       dst[idx] = (jh < P.ny + 2 * HALO && ih < P.pitch)
-                     ? P.qin[(long long) l * P.vstride + (long long) lev * P.zstride + (long long) jh * P.pitch + ih] : 0.0;
+                     ? P.qin[voff(l) + (long long) lev * P.zstride + (long long) jh * P.pitch + ih] : 0.0;
     }
   };
   auto plain_i = [&](int lev) {
@@ -152,7 +158,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     for (int idx = tid; idx < C::ISLOT; idx += C::NTHR) {
       const int l = idx / IPL, c = idx % IPL, jh = j0 + HALO + c / C::IW, ih = i0 + HALO - C::IXO + c % C::IW;
       dst[idx] = (jh < P.ny + 2 * HALO && ih < P.pitch)
-                     ? P.qin[(long long) l * P.vstride + (long long) zplane(lev) * P.zstride + (long long) jh * P.pitch + ih] : 0.0;
+                     ? P.qin[voff(l) + (long long) zplane(lev) * P.zstride + (long long) jh * P.pitch + ih] : 0.0;
     }
   };
   const int nfirst = zper ? NIS : 4;                         // interior planes requested up front: levels -zo .. -zo + nfirst - 1
@@ -295,7 +301,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
     double q0v[N];
     auto load_q0 = [&]() {
 #pragma unroll
-      for (int l = 0; l < N; ++l) q0v[l] = have_q0 ? (PTRS ? q0p[(long long) l * P.vstride] : P.q0[(long long) l * P.vstride + hcell]) : 0.0;
+      for (int l = 0; l < N; ++l) q0v[l] = have_q0 ? (PTRS ? q0p[voff(l)] : P.q0[voff(l) + hcell]) : 0.0;
     };
     if (PTRS) load_q0();
     double prop = 0.0;
@@ -415,7 +421,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
       const double *q = P.qin + (long long) k * P.zstride +
                         (ydir ? (long long) HALO * P.pitch + (ii + HALO) : (long long) (jj + HALO) * P.pitch + HALO);
       double tmp[N];                                         // in local memory (rare path); R itself stays in registers
-      ref1_low_edges(q, ydir ? P.pitch : 1, P.vstride, N, tmp);
+      ref1_low_edges(q, ydir ? P.pitch : 1, P.vstride, troff, N, tmp);
 #pragma unroll
       for (int v = 0; v < N; ++v) R[v] = tmp[v];
       int b = 0;
@@ -533,6 +539,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
       // straight-line: out-of-domain threads of a ragged tile compute on the zero fill and only their stores are masked
 #pragma unroll
       for (int l = 0; l < N; ++l, qo += P.vstride) {
+        if (LBC && l == NUM_STATE) qo += troff;
         {
           const double val_k = Ik[l * IPL];
           double t = tend[l];
@@ -553,7 +560,7 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
               const double qn = (P.rk_a * q0c + P.rk_b * qc) + P.rk_cdt * t;
               out = (l == idT) ? qn : qn * r_new;
             }
-            if (in_dom) qo[0] = out;
+            if (in_dom && put_state) qo[0] = out;
             outv[l] = out;
           } else {
             // tracer: leave the RK base value in qout and the FCT factor in mult for k_tracer_update
@@ -579,12 +586,12 @@ k_stage_cell(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ 
           }
         }
       }
-      if (imgf) {                                            // images at a fixed distance from the cell
+      if (imgf && put_state) {                               // images at a fixed distance from the cell
         double *qi = PTRS ? qop : P.qout + hcell;
 #pragma unroll
         for (int l = 0; l < NUM_STATE; ++l, qi += P.vstride) store_images_fast(P, imgf, qi, outv[l]);
       }
-      if (img) {
+      if (img && put_state) {
         double tmp[NUM_STATE];
 #pragma unroll
         for (int l = 0; l < NUM_STATE; ++l) tmp[l] = outv[l];

@@ -100,7 +100,8 @@ def synthetic_state(g, nz, ny, nx, T, seed):
     s[4] = col[4][:, None, None] + 1.5 * bump
     s[5] = col[5][:, None, None] * (1 + 0.3 * bump)
     for t in range(1, T):
-        blob = np.exp(-(((x - 0.05 - 0.4 * t) ** 2) / 0.005 + ((y - 0.9) ** 2) / 0.02 + ((z - 0.3) ** 2) / 0.02))
+        dxp = (x - (0.05 + 0.4 * t) % 1.0 + 0.5) % 1.0 - 0.5          # periodic distance: the blobs of tracers 3, 4, ... wrap around
+        blob = np.exp(-((dxp ** 2) / 0.005 + ((y - 0.9) ** 2) / 0.02 + ((z - 0.3) ** 2) / 0.02))
         s[5 + t] = 2e-3 * blob * (blob > 0.05)       # compact blobs touching the periodic seam: FCT + clipping active
     s += 0 * rng.random(s.shape)
     return np.ascontiguousarray(s)
@@ -189,6 +190,30 @@ def test_periodic_z_sizes_vs_oracle(golden, nx, ny, T, bc_x, bc_y):
     ref = s0.copy()
     O.dycore_step(p, g["bg"], ref, dt, steps=3)
     out, _ = gpu_run(gg, s0[:5 + T], 3, dt, T, bc_x=bc_x, bc_y=bc_y, bc_z=0)
+    for l in range(5 + T):
+        assert relmax(out[l], ref[l]) <= TOL, (l, relmax(out[l], ref[l]))
+
+
+@pytest.mark.parametrize("nx,ny,T,bc", [(37, 19, 6, {}), (45, 11, 9, {}), (70, 1, 5, {}), (40, 24, 7, dict(bc_x=2, bc_y=1, bc_z=0))])
+def test_more_than_four_tracers_vs_oracle(golden, nx, ny, T, bc):
+    """5 .. 50 tracers (MultipleFields.h:11): one stage launch per group of four tracers, the state stored by the last one.
+    Compact positive blobs (FCT and clipping active in several groups), sub-cycling (two cycles per step), one case with
+    wall x / open y / periodic z"""
+    g = golden("box3d_vapor_dycore5.npz")
+    nz = int(g["nz"])
+    gg = dict(xlen=nx * 1000.0, ylen=max(ny, 1) * 1000.0, zlen=float(g["zlen"]), bg=g["bg"])
+    s0 = synthetic_state(g, nz, ny, nx, T, seed=nx * 100 + ny)
+    dt = 1.5 * 0.6 * min(1000.0, float(g["zlen"]) / nz) / 430.0
+    positive = [1] * T
+    positive[2] = 0                                   # one tracer that may go negative (no FCT, no clipping)
+    adds = [1 if t % 2 == 0 else 0 for t in range(T)]
+    p = O.make_params(nx, ny, nz, gg["xlen"], gg["ylen"], gg["zlen"], T, positive=positive, adds_mass=adds,
+                      ref_single_rank=True, **bc)
+    ref = s0.copy()
+    O.dycore_step(p, g["bg"], ref, dt, steps=2)       # two steps of two sub-cycles each (DYC:104-110)
+    out, launches = gpu_run(gg, s0, 2, dt, T, positive=positive, adds_mass=adds, **bc)
+    ngroups = (T + 3) // 4
+    assert launches == 2 * (2 + 2 * 3 * 2 * ngroups)
     for l in range(5 + T):
         assert relmax(out[l], ref[l]) <= TOL, (l, relmax(out[l], ref[l]))
 

@@ -24,7 +24,7 @@ def _run(nproc, args, port):
     return json.loads(lines[-1])
 
 
-@pytest.mark.parametrize("nproc,nxg,nyg,T,physics", [(2, 40, 36, 1, 0), (2, 50, 1, 3, 0), (2, 36, 40, 3, 1),
+@pytest.mark.parametrize("nproc,nxg,nyg,T,physics", [(2, 40, 36, 1, 0), (2, 50, 1, 3, 0), (2, 36, 40, 3, 1), (2, 40, 36, 6, 0),
                                                      (4, 44, 40, 3, 1), (8, 64, 48, 1, 0)])
 def test_decomposition_independence(nproc, nxg, nyg, T, physics):
     if _ngpu() < nproc:
