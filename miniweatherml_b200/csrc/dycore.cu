@@ -131,6 +131,7 @@ struct mw_dycore {
   bool timing = false;
   std::vector<cudaEvent_t> ev;         // [0]=step begin, [1]=step end, then pairs per stage kernel
   int n_stage_timed = 0;
+  bool timing_valid = true;            // false after a slab-pipelined host step (no events recorded)
 };
 
 // Open / wall lateral boundary on side d (W, E, S, N) of THIS rank's block: the boundary-condition code, else 0
@@ -418,6 +419,7 @@ extern "C" int mw_dycore_enable_timing(mw_dycore *h, int on) {
 
 extern "C" int mw_dycore_last_timing(mw_dycore *h, float *stage_ms, int *n_stage, float *step_ms) {
   MW_REQUIRE(h && h->timing && h->ev.size() >= 2, "timing not enabled or no step taken");
+  MW_REQUIRE(h->timing_valid, "mw_dycore_last_timing: the last step was a slab-pipelined host step, which records no stage events");
   float s = 0, t = 0;
   MW_CUDA_OK(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
   for (int i = 0; i < h->n_stage_timed; ++i) {
@@ -672,6 +674,7 @@ static int step_impl(mw_dycore *h, double *const *fields, double dt_phys, cudaSt
     while (h->ev.size() < n) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
   };
   h->n_stage_timed = 0;
+  h->timing_valid = true;
   if (h->timing) { ensure_events(2); cudaEventRecord(h->ev[0], st); }
 
   Q.S.qout = h->q[0];
@@ -761,6 +764,7 @@ static int step_groups(mw_dycore *h, double *const *fields, double dt_phys, cuda
   Q.R_d = c.R_d; Q.R_v = c.R_v; Q.idWV = c.idWV;
   for (int t = 0; t < T; ++t) if (c.tracer_adds_mass[t]) Q.adds_mass_mask64 |= 1ull << t;
   h->n_stage_timed = 0;
+  h->timing_valid = true;
   if (h->timing) { while (h->ev.size() < 2) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); } cudaEventRecord(h->ev[0], st); }
   Q.S.qout = h->q[0];
   set_images(h, Q.S, 0);
@@ -1076,7 +1080,15 @@ extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields
   const mw_config &c = h->cfg;
   const size_t bytes = (size_t) c.nz * c.ny * c.nx * 8;
   if (!h->dev_fields_alloc) {
-    for (int f = 0; f < h->N; ++f) MW_CUDA_OK(cudaMalloc(&h->dev_fields[f], bytes));
+    for (int f = 0; f < h->N; ++f) {
+      const cudaError_t e = cudaMalloc(&h->dev_fields[f], bytes);
+      if (e != cudaSuccess) {                              // all or nothing: a partial set must not survive the failed call
+        for (int g = 0; g < f; ++g) { cudaFree(h->dev_fields[g]); h->dev_fields[g] = nullptr; }
+        h->dev_fields[f] = nullptr;
+        set_error("mw_dycore_time_step_host: device staging buffers (%zu bytes each): %s", bytes, cudaGetErrorString(e));
+        return MW_ERR_CUDA;
+      }
+    }
     h->dev_fields_alloc = true;
   }
   // slab pipeline: 3-D, equal blocks, and enough rows for >= 4 slabs of whole tile rows with most of a wave of tiles
@@ -1096,6 +1108,7 @@ extern "C" int mw_dycore_time_step_host(mw_dycore *h, double *const *host_fields
   const bool periodic_xy = c.bc_x == MW_BC_PERIODIC && c.bc_y == MW_BC_PERIODIC;     // the slab schedule wraps around the seam
   const bool pipelined = rows_per_slab >= 8 && equal_blocks && periodic_xy && c.num_tracers <= 4 && c.ny_glob > 1 && c.ny / rows_per_slab >= 4;
   if (pipelined) {
+    h->timing_valid = false;                               // the slab pipeline records no stage events: mw_dycore_last_timing says so
     MW_CUDA_OK(cudaDeviceSynchronize());                  // the non-blocking streams do not order against earlier default-stream work
     int rc = 1;
     switch (c.num_tracers) {
