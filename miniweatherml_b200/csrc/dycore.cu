@@ -450,19 +450,25 @@ static int exchange(mw_dycore *h, double *const *send, double *const *recv, cons
 
 // Neighbour barrier of the peer-memory mode: thread d tells the neighbour in direction d "everything I launched before this
 // on my stream is done and visible" (its stores into your halo included) and waits for the same word from it.  A lost
-// neighbour must fail loudly, not hang the GPU: trap after ~10 s of polling.
+// neighbour must fail loudly, not hang the GPU: trap after timeout_ns of polling (MW_PEER_TIMEOUT_S, default 300 s -- long
+// enough for a neighbour that writes output or initialises while this rank already waits in its first barrier).
 __global__ void k_peer_barrier(unsigned long long *mine, unsigned long long *p0, unsigned long long *p1, unsigned long long *p2,
-                               unsigned long long *p3, unsigned long long epoch) {
+                               unsigned long long *p3, unsigned long long epoch, unsigned long long timeout_ns) {
   unsigned long long *peer[4] = {p0, p1, p2, p3};
   const int d = threadIdx.x;
   if (d >= 4 || !peer[d]) return;
   __threadfence_system();
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer[d] + (d ^ 1)), "l"(epoch) : "memory");
-  unsigned long long v = 0;
+  unsigned long long v = 0, t0 = 0;
   for (long long spin = 0;; ++spin) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + d) : "memory");
     if (v >= epoch) break;
-    if (spin > (1ll << 26)) __trap();
+    if ((spin & 1023) == 1023) {                           // look at the clock now and then
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > timeout_ns) __trap();
+    }
     __nanosleep(100);
   }
 }
@@ -470,7 +476,12 @@ static int peer_barrier(mw_dycore *h, cudaStream_t st) {
   ++h->epoch;
   unsigned long long *pf[4];
   for (int d = 0; d < 4; ++d) pf[d] = h->dir_active[d] ? h->peer_mem[d].flags : nullptr;
-  k_peer_barrier<<<1, 32, 0, st>>>(h->flags, pf[0], pf[1], pf[2], pf[3], h->epoch);
+  static const unsigned long long timeout_ns = [] {
+    const char *e = getenv("MW_PEER_TIMEOUT_S");
+    const double sec = (e && atof(e) > 0) ? atof(e) : 300.0;
+    return (unsigned long long) (sec * 1e9);
+  }();
+  k_peer_barrier<<<1, 32, 0, st>>>(h->flags, pf[0], pf[1], pf[2], pf[3], h->epoch, timeout_ns);
   MW_CUDA_OK(cudaGetLastError());
   h->launches++;
   return MW_OK;
