@@ -1149,43 +1149,74 @@ struct PeerInfo {
   long long zstride, vstride;
 };
 }
+// Returns MW_OK with h->peer_halo set, or MW_OK with it unset when some rank could not map a neighbour (GPUs without peer
+// access, IPC unavailable in the container, ...): the decision is collective -- every rank takes part in both NCCL calls
+// whatever happened locally, and all of them fall back to the NCCL exchange together.
 static int setup_peer_halos(mw_dycore *h) {
   const mw_config &c = h->cfg;
   const int nranks = c.nproc_x * c.nproc_y;
-  MW_CUDA_OK(cudaMalloc(&h->flags, 4 * sizeof(unsigned long long)));
-  MW_CUDA_OK(cudaMemset(h->flags, 0, 4 * sizeof(unsigned long long)));
+  bool ok = true;
+  std::string why;
+  auto fail = [&](const char *what, cudaError_t e) { if (ok) { ok = false; why = std::string(what) + ": " + cudaGetErrorString(e); } cudaGetLastError(); };
   PeerInfo mine;
   memset(&mine, 0, sizeof(mine));
-  for (int b = 0; b < 3; ++b) MW_CUDA_OK(cudaIpcGetMemHandle(&mine.q[b], h->q[b]));
-  MW_CUDA_OK(cudaIpcGetMemHandle(&mine.mult, h->mult));
-  MW_CUDA_OK(cudaIpcGetMemHandle(&mine.flags, h->flags));
+  {
+    const char *t = getenv("MW_PEER_TEST_FAIL_RANK");      // tests: pretend this rank cannot map its neighbours
+    if (t && atoi(t) == h->comm->rank) { ok = false; why = "MW_PEER_TEST_FAIL_RANK"; }
+  }
+  cudaError_t e = cudaMalloc(&h->flags, 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->flags, 0, 4 * sizeof(unsigned long long));
+  if (e != cudaSuccess) fail("flag array", e);
+  for (int b = 0; b < 3 && ok; ++b) if ((e = cudaIpcGetMemHandle(&mine.q[b], h->q[b])) != cudaSuccess) fail("cudaIpcGetMemHandle", e);
+  if (ok && (e = cudaIpcGetMemHandle(&mine.mult, h->mult)) != cudaSuccess) fail("cudaIpcGetMemHandle", e);
+  if (ok && (e = cudaIpcGetMemHandle(&mine.flags, h->flags)) != cudaSuccess) fail("cudaIpcGetMemHandle", e);
   mine.nx = c.nx; mine.ny = c.ny; mine.pitch = h->pitch; mine.zstride = h->zstride; mine.vstride = h->vstride;
+  mine.pad = ok ? 1 : 0;                                   // "my handles are valid"
   char *dsend = nullptr, *drecv = nullptr;
+  int *dflag = nullptr;
   MW_CUDA_OK(cudaMalloc(&dsend, sizeof(PeerInfo)));
   MW_CUDA_OK(cudaMalloc(&drecv, sizeof(PeerInfo) * nranks));
+  MW_CUDA_OK(cudaMalloc(&dflag, sizeof(int)));
   MW_CUDA_OK(cudaMemcpy(dsend, &mine, sizeof(PeerInfo), cudaMemcpyHostToDevice));
   MW_NCCL_OK(ncclAllGather(dsend, drecv, sizeof(PeerInfo), ncclChar, h->comm->comm, 0));
   std::vector<PeerInfo> all(nranks);
   MW_CUDA_OK(cudaMemcpy(all.data(), drecv, sizeof(PeerInfo) * nranks, cudaMemcpyDeviceToHost));
-  cudaFree(dsend); cudaFree(drecv);
-  for (int d = 0; d < 4; ++d) {
+  for (int d = 0; d < 4 && ok; ++d) {
     if (!h->dir_active[d]) continue;
     const int r = h->peer[d];
     MW_REQUIRE(r != h->comm->rank, "peer halos: rank %d is its own neighbour in an active direction", r);
     int prev = -1;
-    for (int e = 0; e < d; ++e) if (h->dir_active[e] && h->peer[e] == r) prev = e;
+    for (int q = 0; q < d; ++q) if (h->dir_active[q] && h->peer[q] == r) prev = q;
     mw_dycore::Peer &R = h->peer_mem[d];
     if (prev >= 0) { R = h->peer_mem[prev]; continue; }    // two ranks in a direction: both neighbours are the same process
     const PeerInfo &I = all[r];
-    auto open = [&](const cudaIpcMemHandle_t &hd, void **out) -> cudaError_t {
-      cudaError_t e = cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess);
-      if (e == cudaSuccess) h->ipc_opened.push_back(*out);
-      return e;
+    if (!I.pad) { ok = false; why = "a neighbour has no IPC handles"; break; }
+    auto open = [&](const cudaIpcMemHandle_t &hd, void **out) {
+      if (!ok) return;
+      const cudaError_t oe = cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess);
+      if (oe == cudaSuccess) h->ipc_opened.push_back(*out); else fail("cudaIpcOpenMemHandle", oe);
     };
-    for (int b = 0; b < 3; ++b) MW_CUDA_OK(open(I.q[b], (void **) &R.q[b]));
-    MW_CUDA_OK(open(I.mult, (void **) &R.mult));
-    MW_CUDA_OK(open(I.flags, (void **) &R.flags));
+    for (int b = 0; b < 3; ++b) open(I.q[b], (void **) &R.q[b]);
+    open(I.mult, (void **) &R.mult);
+    open(I.flags, (void **) &R.flags);
     R.nx = I.nx; R.ny = I.ny; R.pitch = I.pitch; R.zstride = I.zstride; R.vstride = I.vstride;
+  }
+  // everybody or nobody
+  int mine_ok = ok ? 1 : 0, all_ok = 0;
+  MW_CUDA_OK(cudaMemcpy(dflag, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
+  MW_NCCL_OK(ncclAllReduce(dflag, dflag, 1, ncclInt, ncclMin, h->comm->comm, 0));
+  MW_CUDA_OK(cudaMemcpy(&all_ok, dflag, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(dsend); cudaFree(drecv); cudaFree(dflag);
+  if (!all_ok) {
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    h->ipc_opened.clear();
+    for (int d = 0; d < 4; ++d) h->peer_mem[d] = mw_dycore::Peer();
+    cudaFree(h->flags); h->flags = nullptr;
+    cudaGetLastError();
+    if (h->comm->rank == 0 || !ok)
+      fprintf(stderr, "[mwb200] rank %d: peer-memory halos unavailable (%s); every rank uses the NCCL exchange\n", h->comm->rank,
+              ok ? "another rank could not map its neighbours" : why.c_str());
+    return MW_OK;
   }
   // x neighbours share my rows, y neighbours my columns (block decomposition, CPL:147-153)
   for (int d = 0; d < 4; ++d) {

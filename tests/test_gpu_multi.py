@@ -33,6 +33,16 @@ def test_decomposition_independence(nproc, nxg, nyg, T, physics):
     assert r["ok"], r
 
 
+def test_peer_halos_fall_back_to_nccl_together(monkeypatch):
+    """one rank cannot map its neighbour's memory (simulated): EVERY rank must take the NCCL exchange -- a split decision
+    would deadlock -- and the answer is unchanged"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("MW_PEER_TEST_FAIL_RANK", "1")
+    r = _run(2, [40, 36, 3, 3, 0], 29791)
+    assert r["ok"], r
+
+
 @pytest.mark.parametrize("nproc,nxg,nyg,T,bc_x,bc_y", [(2, 40, 36, 1, 2, 1), (2, 36, 40, 3, 1, 2), (4, 44, 40, 2, 2, 2), (4, 64, 48, 1, 1, 0),
                                                        (8, 64, 48, 1, 1, 2)])
 def test_lateral_boundaries_on_decomposed_grids(nproc, nxg, nyg, T, bc_x, bc_y):
