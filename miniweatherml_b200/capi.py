@@ -186,6 +186,10 @@ class Dycore:
     def compute_time_step(self):
         return lib().mw_dycore_compute_time_step(self.h)
 
+    def update_lateral_bc(self, bc_x, bc_y):
+        """what coupler.set_option("bc_x" / "bc_y", ...) after init() amounts to (read at every step, DYC:588-589)"""
+        _check(lib().mw_dycore_update_lateral_bc(self.h, int(bc_x), int(bc_y)))
+
     def time_step(self, fields, dt):
         """fields: list of 5+T CUDA fp64 tensors [nz,ny,nx] in coupler order, advanced in place (async)."""
         assert len(fields) == self.N

@@ -218,6 +218,40 @@ def test_more_than_four_tracers_vs_oracle(golden, nx, ny, T, bc):
         assert relmax(out[l], ref[l]) <= TOL, (l, relmax(out[l], ref[l]))
 
 
+def test_lateral_bc_options_take_effect_between_steps(golden):
+    """bc_x / bc_y are re-read at every step (DYC:588-589): a handle created periodic and switched with
+    mw_dycore_update_lateral_bc steps exactly like one created with the new conditions, and back"""
+    import torch
+    import miniweatherml_b200 as mw
+    g = golden("box3d_bc_wall_open_dycore4.npz")
+    nz, ny, nx = g["s0"].shape[1:]
+    dt = float(g["dt"])
+
+    def run(switch):
+        cfg = mw.make_config(nx, ny, nz, float(g["xlen"]), float(g["ylen"]), float(g["zlen"]), 1,
+                             **({} if switch else dict(bc_x=2, bc_y=1)))
+        dy = mw.Dycore(cfg)
+        dy.set_background(g["bg"])
+        if switch:
+            dy.update_lateral_bc(2, 1)
+        f = [torch.tensor(np.ascontiguousarray(g["s0"][l]), device="cuda") for l in range(6)]
+        dy.time_step(f, dt)
+        dy.update_lateral_bc(0, 0)
+        dy.time_step(f, dt)
+        out = np.stack([t.cpu().numpy() for t in f])
+        dy.close()
+        return out
+
+    assert np.array_equal(run(True), run(False))
+    with pytest.raises(mw.MwError):
+        cfg = mw.make_config(nx, ny, nz, 1e3, 1e3, 1e3, 1)
+        dy = mw.Dycore(cfg)
+        try:
+            dy.update_lateral_bc(5, 0)
+        finally:
+            dy.close()
+
+
 def test_lateral_bc_plain_load_path_agrees(golden, monkeypatch):
     g = golden("box3d_bc_wall_open_dycore4.npz")
     a, _ = gpu_run(g, g["s0"], 2, float(g["dt"]), 1, bc_x=2, bc_y=1)
