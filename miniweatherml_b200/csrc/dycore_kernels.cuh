@@ -249,45 +249,60 @@ __device__ __forceinline__ void tracer_finish_cell(const StageParams &P, const C
   const double rho_new = P.qout[hcell] + __ldg(P.hyc + k);
   const long long pl = (long long) P.ny * P.nx;
   double tr_mass[NT > 0 ? NT : 1];
+  // Three passes over the tracers so that every load of the common path is in flight before the first use: (1) face
+  // fluxes, RK base value and tile flags of ALL tracers, (2) arithmetic (the FCT factors are read only where a flag is
+  // set), (3) stores.  One pass per tracer serialised two or three memory round trips per tracer behind its stores.
+  double fxl[NT > 0 ? NT : 1], fxh[NT > 0 ? NT : 1], fyl[NT > 0 ? NT : 1], fyh[NT > 0 ? NT : 1], fzl[NT > 0 ? NT : 1],
+         fzh[NT > 0 ? NT : 1], qb[NT > 0 ? NT : 1], conc[NT > 0 ? NT : 1];
+  int flagged[NT > 0 ? NT : 1];
+  const int tx = i / STAGE_TILE_X, ty = j / STAGE_TILE_Y, xi = i % STAGE_TILE_X, yj = j % STAGE_TILE_Y;
+  // which neighbouring tiles (or neighbour ranks) can put a factor below one on my faces -- the same for every tracer
+  const bool eW = xi == 0, eE = xi == STAGE_TILE_X - 1 || i == P.nx - 1, eS = yj == 0, eN = yj == STAGE_TILE_Y - 1 || j == P.ny - 1;
+  const int rankW = (eW && i == 0 && P.msrc[0].base) ? 1 : 0, rankE = (eE && i == P.nx - 1 && P.msrc[1].base) ? 1 : 0,
+            rankS = (eS && j == 0 && P.msrc[2].base) ? 1 : 0, rankN = (eN && j == P.ny - 1 && P.msrc[3].base) ? 1 : 0;
 #pragma unroll
   for (int tr = 0; tr < NT; ++tr) {
     const double *FXp = P.flux_x + (((long long) tr * P.nz + k) * P.ny + j) * (P.nx + 1) + i;
     const double *FZp = P.flux_z + ((long long) tr * (P.nz + 1) + k) * pl + (long long) j * P.nx + i;
-    const double *Mp = P.mult + (long long) tr * ncell + c;
-    double fxl = FXp[0], fxh = FXp[1], fzl = FZp[0], fzh = FZp[pl], fyl = 0.0, fyh = 0.0;
+    fxl[tr] = FXp[0]; fxh[tr] = FXp[1]; fzl[tr] = FZp[0]; fzh[tr] = FZp[pl]; fyl[tr] = 0.0; fyh[tr] = 0.0;
     if (!P.sim2d) {
       const double *FYp = P.flux_y + (((long long) tr * P.nz + k) * (P.ny + 1) + j) * P.nx + i;
-      fyl = FYp[0]; fyh = FYp[P.nx];
+      fyl[tr] = FYp[0]; fyh[tr] = FYp[P.nx];
     }
-    bool scaled = ((P.positive_mask >> tr) & 1u) != 0;
-    if (scaled) {
+    qb[tr] = P.qout[(long long) (NUM_STATE + tr + P.tr0) * P.vstride + hcell];
+    int f = 0;
+    if ((P.positive_mask >> tr) & 1u) {
       // a factor below one can reach my faces only from my own tile, the tiles next to it when I sit on its edge, or the
       // neighbour rank (whose flags I do not have): otherwise every factor I would read is exactly one
-      const unsigned char *F = P.tflag + (long long) tr * P.tf_nby * P.tf_nbx;
-      const int tx = i / STAGE_TILE_X, ty = j / STAGE_TILE_Y, xi = i % STAGE_TILE_X, yj = j % STAGE_TILE_Y;
-      int f = F[ty * P.tf_nbx + tx];
-      if (xi == 0) f |= (i > 0) ? F[ty * P.tf_nbx + tx - 1] : (P.msrc[0].base != nullptr);
-      if (xi == STAGE_TILE_X - 1 || i == P.nx - 1) f |= (i < P.nx - 1) ? F[ty * P.tf_nbx + tx + 1] : (P.msrc[1].base != nullptr);
-      if (yj == 0) f |= (j > 0) ? F[(ty - 1) * P.tf_nbx + tx] : (P.msrc[2].base != nullptr);
-      if (yj == STAGE_TILE_Y - 1 || j == P.ny - 1) f |= (j < P.ny - 1) ? F[(ty + 1) * P.tf_nbx + tx] : (P.msrc[3].base != nullptr);
-      scaled = f != 0;
+      const unsigned char *F = P.tflag + (long long) tr * P.tf_nby * P.tf_nbx + ty * P.tf_nbx + tx;
+      f = F[0] | rankW | rankE | rankS | rankN;
+      if (eW && i > 0) f |= F[-1];
+      if (eE && i < P.nx - 1) f |= F[1];
+      if (eS && j > 0) f |= F[-P.tf_nbx];
+      if (eN && j < P.ny - 1) f |= F[P.tf_nbx];
     }
-    if (scaled) {
-      const double ms = Mp[0];
-      if (fxl > 0) { if (i > 0) fxl *= Mp[-1]; else if (P.msrc[0].base) fxl *= neighbour_mult(P, 0, tr, k, j); }             else if (fxl < 0) fxl *= ms;
-      if (fxh < 0) { if (i < P.nx - 1) fxh *= Mp[1]; else if (P.msrc[1].base) fxh *= neighbour_mult(P, 1, tr, k, j); }       else if (fxh > 0) fxh *= ms;
-      if (fyl > 0) { if (j > 0) fyl *= Mp[-P.nx]; else if (P.msrc[2].base) fyl *= neighbour_mult(P, 2, tr, k, i); }          else if (fyl < 0) fyl *= ms;
-      if (fyh < 0) { if (j < P.ny - 1) fyh *= Mp[P.nx]; else if (P.msrc[3].base) fyh *= neighbour_mult(P, 3, tr, k, i); }    else if (fyh > 0) fyh *= ms;
-      if (fzl > 0) { if (k > 0) fzl *= Mp[-pl]; }                else if (fzl < 0) fzl *= ms;
-      if (fzh < 0) { if (k < P.nz - 1) fzh *= Mp[pl]; }          else if (fzh > 0) fzh *= ms;
-    }
-    const double t = -(fxh - fxl) * P.rdx - (fyh - fyl) * P.rdy - (fzh - fzl) * P.rdz;
-    double qn = P.qout[(long long) (NUM_STATE + tr + P.tr0) * P.vstride + hcell] + P.rk_cdt * t;
-    if ((P.positive_mask >> tr) & 1u) qn = fmax(0.0, qn);
-    const double conc = qn / rho_new;                    // IEEE division: keeps the tracer-mass round trip unbiased
-    store_with_images(P, NUM_STATE + tr + P.tr0, k, j, i, conc);
-    if (D2C) tr_mass[tr] = conc * rho_new;
+    flagged[tr] = f;
   }
+#pragma unroll
+  for (int tr = 0; tr < NT; ++tr) {
+    if (flagged[tr]) {
+      const double *Mp = P.mult + (long long) tr * ncell + c;
+      const double ms = Mp[0];
+      if (fxl[tr] > 0) { if (i > 0) fxl[tr] *= Mp[-1]; else if (P.msrc[0].base) fxl[tr] *= neighbour_mult(P, 0, tr, k, j); }             else if (fxl[tr] < 0) fxl[tr] *= ms;
+      if (fxh[tr] < 0) { if (i < P.nx - 1) fxh[tr] *= Mp[1]; else if (P.msrc[1].base) fxh[tr] *= neighbour_mult(P, 1, tr, k, j); }       else if (fxh[tr] > 0) fxh[tr] *= ms;
+      if (fyl[tr] > 0) { if (j > 0) fyl[tr] *= Mp[-P.nx]; else if (P.msrc[2].base) fyl[tr] *= neighbour_mult(P, 2, tr, k, i); }          else if (fyl[tr] < 0) fyl[tr] *= ms;
+      if (fyh[tr] < 0) { if (j < P.ny - 1) fyh[tr] *= Mp[P.nx]; else if (P.msrc[3].base) fyh[tr] *= neighbour_mult(P, 3, tr, k, i); }    else if (fyh[tr] > 0) fyh[tr] *= ms;
+      if (fzl[tr] > 0) { if (k > 0) fzl[tr] *= Mp[-pl]; }                else if (fzl[tr] < 0) fzl[tr] *= ms;
+      if (fzh[tr] < 0) { if (k < P.nz - 1) fzh[tr] *= Mp[pl]; }          else if (fzh[tr] > 0) fzh[tr] *= ms;
+    }
+    const double t = -(fxh[tr] - fxl[tr]) * P.rdx - (fyh[tr] - fyl[tr]) * P.rdy - (fzh[tr] - fzl[tr]) * P.rdz;
+    double qn = qb[tr] + P.rk_cdt * t;
+    if ((P.positive_mask >> tr) & 1u) qn = fmax(0.0, qn);
+    conc[tr] = qn / rho_new;                             // IEEE division: keeps the tracer-mass round trip unbiased
+    if (D2C) tr_mass[tr] = conc[tr] * rho_new;
+  }
+#pragma unroll
+  for (int tr = 0; tr < NT; ++tr) store_with_images(P, NUM_STATE + tr + P.tr0, k, j, i, conc[tr]);
   if (D2C) {
     const ConvertParams &Q = *Qp;
     const double rt = P.qout[(long long) idT * P.vstride + hcell] + __ldg(P.hytc + k);
