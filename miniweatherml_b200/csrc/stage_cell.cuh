@@ -13,7 +13,15 @@
 //   * there are no job tables, no inner loops and no role hand-offs: two CTA barriers per level.
 // The 1-cell ring of reconstructions around the tile (its outer faces need the far side's edge values) is dealt out as
 // single-variable jobs, two per thread and level.  Planes arrive by TMA: per level one haloed box {38, 14, 1, N} for
-// the x / y stencils (two slots) and one interior box {32, 8, 1, N} for the z windows (five slots).
+// the x / y stencils (two slots) and one interior box {34, 8, 1, N} for the z windows (five slots).
+//
+// What limits it.  The reconstruction blocks run the FP64 pipe at ~90 %; everything else is
+// fixed-latency code at two warps per scheduler, so instructions removed there pay about one for one and FP64-pipe
+// utilisation is the SUM of what each warp can issue -- an attempt to run the two halves of the tile half a level apart
+// ("ping-pong", profiles/r02o_*) lost for that reason.  Rare paths (images with other strides, boundary conditions, the
+// equation-of-state repair, mbarrier polling) are out of line on purpose: inlined they cost instruction-cache misses.
+// Instantiations: <NT, TMA, LBC> -- LBC = open / wall lateral boundaries, periodic z and the tracer groups of runs with more
+// than four tracers; the periodic default carries none of that code.
 #pragma once
 #include "dycore_kernels.cuh"
 
